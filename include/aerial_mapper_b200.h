@@ -1,0 +1,194 @@
+/*
+ * aerial_mapper_b200.h — C ABI of the B200-native grid-mapping hot path.
+ *
+ * This is the drop-in boundary for the ONE data-parallel path of ethz-asl/aerial_mapper:
+ *   - dsm::Dsm::process                       (reference aerial_mapper_dsm/src/dsm.cc:186-201, cell loop :113-184)
+ *   - ortho::OrthoBackwardGrid::process       (reference aerial_mapper_ortho/src/ortho-backward-grid.cc:223-239,
+ *                                              cell loop :128-221)
+ * The reference has no FFI layer of its own: its boundary is those two C++ classes operating on a
+ * grid_map::GridMap (float32, column-major layers).  The C++ shim under aerial_mapper_b200/shim/ re-creates the
+ * two classes with the reference signatures and marshals to the functions below; the Python mirror
+ * (aerial_mapper_b200/api.py) binds the same functions through ctypes.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - Layers are float32, column-major, `rows x cols` with rows = size(0) (x / easting, Eigen row index) and
+ *     cols = size(1) (y / northing); element (i,j) lives at `i + j*rows`
+ *     (grid_map::Matrix = Eigen::MatrixXf, reference aerial-mapper-grid-map.cc:25-48).
+ *   - A context owns ONE device and ONE contiguous column stripe [col_begin, col_end) of the map (a slab of
+ *     rows*(col_end-col_begin) floats per layer).  A single-GPU context owns [0, cols).
+ *   - Every function returns AMB_OK (0) or a negative amb_status.  The reference aborts through glog CHECK on
+ *     contract violations; the shim turns a non-zero status back into that behaviour.
+ *   - Entry points taking HOST pointers are synchronous (like the reference's blocking process()).
+ *     `_device` entry points take device pointers valid on the context's device, enqueue on the context's
+ *     stream and return without synchronising; call amb_sync() before reading results.
+ */
+#ifndef AERIAL_MAPPER_B200_H_
+#define AERIAL_MAPPER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMB_ABI_VERSION 1
+
+typedef enum amb_status {
+  AMB_OK = 0,
+  AMB_ERR_EMPTY = -1,            /* empty point cloud / no frames (dsm.cc:189-192 warns+returns; ortho CHECKs) */
+  AMB_ERR_SIZE_MISMATCH = -2,    /* poses vs images count, stripe bounds, layer sizes */
+  AMB_ERR_COINCIDENT_POINT = -3, /* a point lies exactly on a cell centre: reference CHECK(distances[i] > 0) dsm.cc:165 */
+  AMB_ERR_CUDA = -4,
+  AMB_ERR_INVALID_ARGUMENT = -5,
+  AMB_ERR_CHECK_FAILED = -6,     /* reference CHECK(alpha > 0.0), ortho-backward-grid.cc:178 */
+  AMB_ERR_NO_DEVICE = -7,
+  AMB_ERR_UNSUPPORTED = -8
+} amb_status;
+
+/* Geometry of the grid_map (grid_map::GridMap::setGeometry as called at aerial-mapper-grid-map.cc:30-33). */
+typedef struct amb_geometry {
+  int32_t rows;        /* size(0) = round(length_x_requested / resolution) */
+  int32_t cols;        /* size(1) */
+  double resolution;   /* metres per cell */
+  double length_x;     /* rows * resolution */
+  double length_y;     /* cols * resolution */
+  double pos_x;        /* map centre, x = easting  */
+  double pos_y;        /* map centre, y = northing */
+} amb_geometry;
+
+/* Layer ids in the order AerialGridMap creates them (aerial-mapper-grid-map.cc:25-28). */
+typedef enum amb_layer_id {
+  AMB_LAYER_ORTHO = 0,
+  AMB_LAYER_ELEVATION = 1,
+  AMB_LAYER_ELEVATION_ANGLE = 2,
+  AMB_LAYER_NUM_OBSERVATIONS = 3,
+  AMB_LAYER_ELEVATION_ANGLE_FIRST_VIEW = 4,
+  AMB_LAYER_DELTA = 5,
+  AMB_LAYER_OBSERVATION_INDEX = 6,
+  AMB_LAYER_OBSERVATION_INDEX_FIRST = 7,
+  AMB_LAYER_COLORED_ORTHO = 8,
+  AMB_NUM_LAYERS = 9
+} amb_layer_id;
+
+/* Camera 0 of the aslam::NCamera rig (ortho-backward-grid.cc:131,232): pinhole + distortion + T_C_B. */
+typedef enum amb_distortion {
+  AMB_DIST_NONE = 0,
+  AMB_DIST_RADTAN = 1,       /* k1 k2 p1 p2 */
+  AMB_DIST_EQUIDISTANT = 2   /* k1 k2 k3 k4 */
+} amb_distortion;
+
+typedef struct amb_camera {
+  int32_t width, height;     /* imageWidth(), imageHeight() */
+  double fu, fv, cu, cv;     /* pinhole intrinsics */
+  int32_t dist_type;         /* amb_distortion */
+  int32_t reserved_;
+  double dist[4];
+  double q_C_B[4];           /* rotation of T_C_B as unit quaternion (w, x, y, z) */
+  double t_C_B[3];           /* translation of T_C_B */
+} amb_camera;
+
+/* Device-side stage timings of the last process call, CUDA events on the context's stream (milliseconds). */
+typedef struct amb_timings {
+  float dsm_h2d_ms;      /* host->device copy of the points (host entry point only) */
+  float dsm_bin_ms;      /* bin count + scan + scatter + in-bin canonical ordering */
+  float dsm_gather_ms;   /* tile IDW gather kernel (the dominant DSM kernel) */
+  float dsm_fill_ms;     /* expanding-radius hole fill kernel */
+  float dsm_total_ms;
+  float ortho_h2d_ms;    /* host->device copy of the frames (host entry point only) */
+  float ortho_kernel_ms; /* project/select/gather kernel(s) */
+  float ortho_total_ms;
+  int32_t dsm_kernel_launches;
+  int32_t ortho_kernel_launches;
+  int64_t dsm_points_binned;  /* points that fell inside the stripe + halo */
+  int64_t dsm_cells_empty;    /* cells that entered the hole-fill pass */
+} amb_timings;
+
+typedef struct amb_ctx amb_ctx;
+
+/* ---- library ---- */
+int amb_abi_version(void);
+const char* amb_status_string(int status);
+/* Last CUDA/driver error text recorded on this context (never NULL). */
+const char* amb_last_error(const amb_ctx* ctx);
+/* Number of CUDA devices visible; negative amb_status on failure. */
+int amb_device_count(void);
+
+/* ---- geometry ---- */
+/* grid_map::GridMap::setGeometry(Length(delta_easting, delta_northing), resolution, Position(center_easting,
+ * center_northing)) as AerialGridMap::initialize calls it (aerial-mapper-grid-map.cc:30-33):
+ * size = round(length / resolution), length = size * resolution. */
+int amb_geometry_init(double delta_easting, double delta_northing, double resolution, double center_easting,
+                      double center_northing, amb_geometry* out);
+/* grid_map::GridMap::getPosition(Index(i, j)) (call sites dsm.cc:124-125, ortho-backward-grid.cc:149-150). */
+int amb_geometry_position(const amb_geometry* geom, int32_t i, int32_t j, double* x, double* y);
+
+/* ---- context ---- */
+/* Create a context on `device` owning columns [col_begin, col_end) of the map.  Pass 0, geom->cols for the
+ * whole map.  Device layer slabs are allocated lazily (first upload / init / process that touches them). */
+int amb_create(const amb_geometry* geom, int device, int32_t col_begin, int32_t col_end, amb_ctx** out);
+void amb_destroy(amb_ctx* ctx);
+int amb_sync(amb_ctx* ctx);
+/* The cudaStream_t the context enqueues on (as an opaque pointer), so callers holding device buffers can order
+ * their own work against it. */
+void* amb_stream(amb_ctx* ctx);
+
+/* Set every layer slab to the value AerialGridMap::initialize gives it (aerial-mapper-grid-map.cc:40-48):
+ * ortho=255, elevation=NaN, elevation_angle=0, num_observations=0, the rest NaN. */
+int amb_init_layers(amb_ctx* ctx);
+/* Copy one layer slab host->device / device->host.  `host_slab` points at element (0, col_begin), i.e. the
+ * caller offsets a full-map pointer by rows*col_begin; rows*(col_end-col_begin) floats are moved. */
+int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab);
+int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab);
+/* Device pointer of a layer slab (allocating it if needed), for device-side consumers (NCCL all-gather of
+ * finished stripes, downstream kernels). */
+int amb_layer_device_ptr(amb_ctx* ctx, int layer, float** device_slab);
+
+/* ---- DSM: dsm::Dsm::process (dsm.cc:186-201) ---- */
+/* xyz: n points, array-of-structs double[3], 24-byte stride — the memory layout of
+ * AlignedType<std::vector, Eigen::Vector3d>::type (dsm.h:41-43).  interpolation_radius, center_easting and
+ * center_northing are the dsm::Settings fields (dsm.h:25-32); the radius is an int compared against SQUARED
+ * distances in m^2 (nanoflann RadiusResultSet, nanoflann.hpp:156-158).  n == 0 returns AMB_ERR_EMPTY and leaves
+ * the elevation layer untouched (dsm.cc:189-192).  Result: the context's `elevation` slab. */
+int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpolation_radius,
+                    double center_easting, double center_northing);
+int amb_dsm_process_device(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius,
+                           double center_easting, double center_northing);
+/* Ask the next amb_dsm_process* calls to also record, per cell of the slab, the number of neighbours that
+ * entered the IDW sum (result_set.size(), dsm.cc:146) and the index k of the threshold lambda_k*radius that
+ * produced them (0 = first query succeeded, 1.. = expanding-radius retries dsm.cc:133-144, -1 = cell untouched). */
+int amb_dsm_enable_debug(amb_ctx* ctx, int enable);
+int amb_dsm_download_debug(amb_ctx* ctx, int32_t* neighbour_count, int8_t* threshold_index);
+/* The thresholds lambda_k * radius the reference's retry loop visits (dsm.cc:133-144), computed with its exact
+ * recurrence.  Returns the count (<= capacity) or a negative status. */
+int amb_dsm_thresholds(int32_t interpolation_radius, double* thresholds, int32_t capacity);
+
+/* ---- Orthomosaic: ortho::OrthoBackwardGrid::process (ortho-backward-grid.cc:223-239) ---- */
+/* T_G_B: n poses, 7 doubles each in the order of the reference's pose files: x y z qw qx qy qz
+ * (aerial-mapper-io.cc:110).  images: n host pointers to H x W x channels uint8 rasters with `row_step` bytes
+ * per row (cv::Mat data/step); channels = 1 (CV_8UC1) or 3 (CV_8UC3, B,G,R byte order).  colored_ortho is
+ * ortho::Settings::colored_ortho (ortho-backward-grid.h:39): non-zero writes the packed 0x00RRGGBB bit pattern
+ * to `colored_ortho` and requires channels == 3, zero writes the gray value to `ortho` and requires
+ * channels == 1.  Reads `elevation`; read-modify-writes `elevation_angle`; writes `observation_index`. */
+int amb_ortho_process(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* images,
+                      size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
+/* Same with frames already resident on the context's device: d_images[i] are DEVICE pointers (the pointer
+ * array itself is in host memory). */
+int amb_ortho_process_device(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B,
+                             const uint8_t* const* d_images, size_t n, int32_t channels, size_t row_step,
+                             int32_t colored_ortho);
+/* 0 = cull frames per tile with the conservative view-cone test (default), 1 = brute force over all frames
+ * (the cull's own correctness reference). */
+int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force);
+
+/* ---- measurement ---- */
+int amb_get_timings(amb_ctx* ctx, amb_timings* out);
+
+/* Pinned host memory for callers that want full-rate host<->device copies inside process(). */
+int amb_host_alloc(void** ptr, size_t bytes);
+int amb_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AERIAL_MAPPER_B200_H_ */

@@ -1,0 +1,196 @@
+"""ctypes binding of the CPU oracle — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module
+(see oracle/amb_oracle.h).  The product package `aerial_mapper_b200` never does.
+
+PARITY UNPINNED: the reference holds no golden vectors for this path; see amb_oracle.h for what
+pins the oracle instead.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "libamb_oracle_ref.so")
+_REFERENCE_ROOT = "/root/reference"
+
+
+class Geometry(C.Structure):
+    """amb_geometry (include/aerial_mapper_b200.h)."""
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("resolution", C.c_double),
+                ("length_x", C.c_double), ("length_y", C.c_double), ("pos_x", C.c_double), ("pos_y", C.c_double)]
+
+
+class Camera(C.Structure):
+    """amb_camera (include/aerial_mapper_b200.h)."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fu", C.c_double), ("fv", C.c_double),
+                ("cu", C.c_double), ("cv", C.c_double), ("dist_type", C.c_int32), ("reserved_", C.c_int32),
+                ("dist", C.c_double * 4), ("q_C_B", C.c_double * 4), ("t_C_B", C.c_double * 3)]
+
+
+def build(force=False):
+    """Compile liboracle.so (always possible) and oracle/_ref (only where /root/reference exists)."""
+    need = force or not os.path.exists(_LIB_PATH)
+    srcs = ["dsm_oracle.cc", "ortho_oracle.cc", "dsm_cell_loop.h", "oracle_common.h", "amb_oracle.h"]
+    if not need:
+        t = os.path.getmtime(_LIB_PATH)
+        need = any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in srcs)
+    if need:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir(_REFERENCE_ROOT):
+        need_ref = force or not os.path.exists(_REF_PATH)
+        if not need_ref:
+            t = os.path.getmtime(_REF_PATH)
+            need_ref = any(os.path.getmtime(os.path.join(_HERE, s)) > t
+                           for s in ["ref_nanoflann_dsm.cc", "dsm_cell_loop.h", "oracle_common.h"])
+        if need_ref:
+            subprocess.check_call(["make", "-C", _HERE, "-B", "ref"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+_DSM_ARGS = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_double, C.c_double,
+             C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.ambo_dsm_process.argtypes = _DSM_ARGS
+        L.ambo_dsm_process.restype = C.c_int
+        L.ambo_ortho_process.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_int32, C.c_size_t, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                         C.c_void_p]
+        L.ambo_ortho_process.restype = C.c_int
+        L.ambo_project3.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p]
+        L.ambo_project3.restype = C.c_int
+        L.ambo_transform_to_camera.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ambo_transform_to_camera.restype = C.c_int
+        L.ambo_pack_color.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8]
+        L.ambo_pack_color.restype = C.c_uint32
+        L.ambo_hardware_concurrency.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def have_ref():
+    if os.path.isdir(_REFERENCE_ROOT):
+        build()
+    return os.path.exists(_REF_PATH)
+
+
+def ref():
+    """oracle/_ref: the cell loop around the reference's own nanoflann.hpp (None if it was never built)."""
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            return None
+        L = C.CDLL(_REF_PATH)
+        L.ambo_ref_dsm_process.argtypes = _DSM_ARGS
+        L.ambo_ref_dsm_process.restype = C.c_int
+        _ref = L
+    return _ref
+
+
+def make_geometry(rows, cols, resolution, pos_x=0.0, pos_y=0.0):
+    return Geometry(int(rows), int(cols), float(resolution), rows * float(resolution), cols * float(resolution),
+                    float(pos_x), float(pos_y))
+
+
+def make_camera(width, height, fu, fv, cu, cv, dist_type=0, dist=(0, 0, 0, 0), q_C_B=(1, 0, 0, 0),
+                t_C_B=(0, 0, 0)):
+    cam = Camera()
+    cam.width, cam.height = int(width), int(height)
+    cam.fu, cam.fv, cam.cu, cam.cv = float(fu), float(fv), float(cu), float(cv)
+    cam.dist_type = int(dist_type)
+    cam.dist = (C.c_double * 4)(*[float(d) for d in dist])
+    cam.q_C_B = (C.c_double * 4)(*[float(d) for d in q_C_B])
+    cam.t_C_B = (C.c_double * 3)(*[float(d) for d in t_C_B])
+    return cam
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def dsm_process(geom, elevation, xyz, radius=1, center_easting=0.0, center_northing=0.0, num_threads=0,
+                cell_range=None, debug=False, use_ref=False):
+    """Run the oracle DSM on `elevation` (float32 F-order rows x cols, modified in place).
+
+    Returns (status, neighbour_count|None, threshold_index|None, seconds[2])."""
+    assert elevation.dtype == np.float32 and elevation.flags.f_contiguous
+    assert elevation.shape == (geom.rows, geom.cols)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n = xyz.shape[0] if xyz.ndim == 2 else xyz.size // 3
+    total = geom.rows * geom.cols
+    lo, hi = (0, total) if cell_range is None else cell_range
+    cnt = np.full(total, -1, np.int32) if debug else None
+    lvl = np.full(total, -1, np.int8) if debug else None
+    sec = np.zeros(2, np.float64)
+    fn = ref().ambo_ref_dsm_process if use_ref else lib().ambo_dsm_process
+    st = fn(C.byref(geom), _ptr(elevation), _ptr(xyz), n, int(radius), float(center_easting),
+            float(center_northing), int(num_threads), lo, hi, _ptr(cnt), _ptr(lvl), _ptr(sec))
+    if debug:
+        cnt = cnt.reshape((geom.rows, geom.cols), order="F")
+        lvl = lvl.reshape((geom.rows, geom.cols), order="F")
+    return st, cnt, lvl, sec
+
+
+def ortho_process(geom, layers, camera, T_G_B, images, colored=False, num_threads=0, cell_range=None):
+    """Run the oracle orthomosaic.  layers: dict of float32 F-order arrays (elevation, elevation_angle,
+    observation_index, ortho, colored_ortho), modified in place.  images: list of uint8 arrays HxW or HxWx3 (BGR).
+
+    Returns (status, seconds)."""
+    T = np.ascontiguousarray(T_G_B, dtype=np.float64).reshape(-1, 7)
+    n = T.shape[0]
+    assert len(images) == n
+    imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    channels = 3 if colored else 1
+    h, w = imgs[0].shape[:2]
+    for im in imgs:
+        assert im.shape[:2] == (h, w) and (im.ndim == 3 and im.shape[2] == 3 if colored else im.ndim == 2)
+    row_step = w * channels
+    ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    total = geom.rows * geom.cols
+    lo, hi = (0, total) if cell_range is None else cell_range
+    for k in ("elevation", "elevation_angle", "observation_index"):
+        a = layers[k]
+        assert a.dtype == np.float32 and a.flags.f_contiguous and a.shape == (geom.rows, geom.cols), k
+    sec = np.zeros(1, np.float64)
+    st = lib().ambo_ortho_process(C.byref(geom), _ptr(layers["elevation"]), _ptr(layers["elevation_angle"]),
+                                  _ptr(layers["observation_index"]), _ptr(layers.get("ortho")),
+                                  _ptr(layers.get("colored_ortho")), C.byref(camera), _ptr(T),
+                                  C.cast(ptrs, C.c_void_p), n, channels, row_step, 1 if colored else 0,
+                                  int(num_threads), lo, hi, _ptr(sec))
+    return st, float(sec[0])
+
+
+def project3(camera, p_C):
+    p = np.ascontiguousarray(p_C, dtype=np.float64)
+    kp = np.zeros(2, np.float64)
+    vis = lib().ambo_project3(C.byref(camera), _ptr(p), _ptr(kp))
+    return bool(vis), kp
+
+
+def transform_to_camera(camera, T_G_B_row, p_G):
+    T = np.ascontiguousarray(T_G_B_row, dtype=np.float64)
+    p = np.ascontiguousarray(p_G, dtype=np.float64)
+    out = np.zeros(3, np.float64)
+    lib().ambo_transform_to_camera(C.byref(camera), _ptr(T), _ptr(p), _ptr(out))
+    return out
+
+
+def pack_color(b, g, r):
+    return int(lib().ambo_pack_color(int(b), int(g), int(r)))
+
+
+def hardware_concurrency():
+    return int(lib().ambo_hardware_concurrency())
