@@ -1,0 +1,378 @@
+// amb_api.cu — the extern "C" boundary (include/aerial_mapper_b200.h): context, layers, host entry points.
+#include <cmath>
+#include <limits>
+#include <new>
+
+#include "amb_context.h"
+
+namespace amb {
+
+__global__ void fill_kernel(float* p, size_t n, float v) {
+  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[k] = v;
+}
+
+int ensure_layer(amb_ctx* ctx, int layer) {
+  if (layer < 0 || layer >= AMB_NUM_LAYERS) return AMB_ERR_INVALID_ARGUMENT;
+  if (ctx->layers[layer]) return AMB_OK;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  float* p = nullptr;
+  AMB_CUDA(ctx, cudaMalloc(&p, ctx->slab_cells() * sizeof(float)));
+  ctx->layers[layer] = p;
+  // A layer that was never uploaded starts with AerialGridMap's initial value (aerial-mapper-grid-map.cc:40-48).
+  float v = std::numeric_limits<float>::quiet_NaN();
+  if (layer == AMB_LAYER_ORTHO) v = 255.0f;
+  if (layer == AMB_LAYER_ELEVATION_ANGLE || layer == AMB_LAYER_NUM_OBSERVATIONS) v = 0.0f;
+  fill_kernel<<<kNumSMsB200 * 4, 256, 0, ctx->stream>>>(p, ctx->slab_cells(), v);
+  AMB_CUDA(ctx, cudaGetLastError());
+  return AMB_OK;
+}
+
+static int finish_flags(amb_ctx* ctx, unsigned int offset_words, int err_code) {
+  unsigned int flag = 0;
+  AMB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->counters.as<unsigned int>() + offset_words, sizeof(flag),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return flag ? err_code : AMB_OK;
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" {
+
+int amb_abi_version(void) { return AMB_ABI_VERSION; }
+
+const char* amb_status_string(int status) {
+  switch (status) {
+    case AMB_OK: return "ok";
+    case AMB_ERR_EMPTY: return "empty input";
+    case AMB_ERR_SIZE_MISMATCH: return "size mismatch";
+    case AMB_ERR_COINCIDENT_POINT: return "a point coincides with a cell centre (reference CHECK(distances[i] > 0.0))";
+    case AMB_ERR_CUDA: return "CUDA error";
+    case AMB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case AMB_ERR_CHECK_FAILED: return "reference CHECK(alpha > 0.0) failed";
+    case AMB_ERR_NO_DEVICE: return "no CUDA device";
+    case AMB_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+const char* amb_last_error(const amb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int amb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return AMB_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+int amb_geometry_init(double delta_easting, double delta_northing, double resolution, double center_easting,
+                      double center_northing, amb_geometry* out) {
+  if (!out || !(resolution > 0.0) || !(delta_easting > 0.0) || !(delta_northing > 0.0))
+    return AMB_ERR_INVALID_ARGUMENT;
+  // grid_map::GridMap::setGeometry: size = round(length / resolution); length = size * resolution.
+  out->rows = static_cast<int32_t>(std::round(delta_easting / resolution));
+  out->cols = static_cast<int32_t>(std::round(delta_northing / resolution));
+  if (out->rows <= 0 || out->cols <= 0) return AMB_ERR_INVALID_ARGUMENT;
+  out->resolution = resolution;
+  out->length_x = out->rows * resolution;
+  out->length_y = out->cols * resolution;
+  out->pos_x = center_easting;
+  out->pos_y = center_northing;
+  return AMB_OK;
+}
+
+int amb_geometry_position(const amb_geometry* g, int32_t i, int32_t j, double* x, double* y) {
+  if (!g || !x || !y) return AMB_ERR_INVALID_ARGUMENT;
+  if (i < 0 || j < 0 || i >= g->rows || j >= g->cols) return AMB_ERR_SIZE_MISMATCH;
+  // grid_map::getPositionFromIndex: (mapPosition + (0.5*length - 0.5*res)) + res * (-(double)index)
+  *x = (g->pos_x + (0.5 * g->length_x - 0.5 * g->resolution)) + g->resolution * (-static_cast<double>(i));
+  *y = (g->pos_y + (0.5 * g->length_y - 0.5 * g->resolution)) + g->resolution * (-static_cast<double>(j));
+  return AMB_OK;
+}
+
+int amb_create(const amb_geometry* geom, int device, int32_t col_begin, int32_t col_end, amb_ctx** out) {
+  if (!geom || !out) return AMB_ERR_INVALID_ARGUMENT;
+  if (geom->rows <= 0 || geom->cols <= 0 || !(geom->resolution > 0.0)) return AMB_ERR_INVALID_ARGUMENT;
+  if (col_begin < 0 || col_end > geom->cols || col_begin >= col_end) return AMB_ERR_SIZE_MISMATCH;
+  if (static_cast<size_t>(geom->rows) * static_cast<size_t>(col_end - col_begin) >= size_t(0xffffffffu))
+    return AMB_ERR_UNSUPPORTED;
+  int n = amb_device_count();
+  if (n <= 0) return AMB_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return AMB_ERR_INVALID_ARGUMENT;
+  amb_ctx* ctx = new (std::nothrow) amb_ctx();
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->geom = *geom;
+  ctx->device = device;
+  ctx->col_begin = col_begin;
+  ctx->col_end = col_end;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < EV_COUNT && e == cudaSuccess; ++k) e = cudaEventCreate(&ctx->events[k]);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ctx->copy_done[k], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    amb_destroy(ctx);
+    return AMB_ERR_CUDA;
+  }
+  *out = ctx;
+  return AMB_OK;
+}
+
+void amb_destroy(amb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int l = 0; l < AMB_NUM_LAYERS; ++l)
+    if (ctx->layers[l]) cudaFree(ctx->layers[l]);
+  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->records,   &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
+                          &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
+                          &ctx->frame_cull};
+  for (DeviceBuffer* b : bufs) b->release();
+  for (int k = 0; k < EV_COUNT; ++k)
+    if (ctx->events[k]) cudaEventDestroy(ctx->events[k]);
+  for (int k = 0; k < 2; ++k)
+    if (ctx->copy_done[k]) cudaEventDestroy(ctx->copy_done[k]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+int amb_sync(amb_ctx* ctx) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // Deferred reference CHECKs of the asynchronous `_device` entry points.
+  if (ctx->counters.ptr) {
+    unsigned int c[16];
+    AMB_CUDA(ctx, cudaMemcpy(c, ctx->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
+    if (c[1]) return AMB_ERR_COINCIDENT_POINT;
+    if (c[8]) return AMB_ERR_CHECK_FAILED;
+  }
+  return AMB_OK;
+}
+
+void* amb_stream(amb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
+int amb_init_layers(amb_ctx* ctx) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  for (int l = 0; l < AMB_NUM_LAYERS; ++l) {
+    // Slabs are allocated lazily and a fresh slab is born with its initial value (ensure_layer), so only the
+    // ones that already exist need refilling.
+    if (!ctx->layers[l]) continue;
+    float v = nan;
+    if (l == AMB_LAYER_ORTHO) v = 255.0f;
+    if (l == AMB_LAYER_ELEVATION_ANGLE || l == AMB_LAYER_NUM_OBSERVATIONS) v = 0.0f;
+    fill_kernel<<<kNumSMsB200 * 4, 256, 0, ctx->stream>>>(ctx->layers[l], ctx->slab_cells(), v);
+  }
+  AMB_CUDA(ctx, cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab) {
+  if (!ctx || !host_slab) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int st = ensure_layer(ctx, layer);
+  if (st != AMB_OK) return st;
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->layers[layer], host_slab, ctx->slab_cells() * sizeof(float),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMB_OK;
+}
+
+int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab) {
+  if (!ctx || !host_slab) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int st = ensure_layer(ctx, layer);
+  if (st != AMB_OK) return st;
+  AMB_CUDA(ctx, cudaMemcpyAsync(host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMB_OK;
+}
+
+int amb_layer_device_ptr(amb_ctx* ctx, int layer, float** device_slab) {
+  if (!ctx || !device_slab) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int st = ensure_layer(ctx, layer);
+  if (st != AMB_OK) return st;
+  *device_slab = ctx->layers[layer];
+  return AMB_OK;
+}
+
+// ---- DSM ----
+int amb_dsm_process_device(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius,
+                           double center_easting, double center_northing) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;  // dsm.cc:189-192
+  if (!d_xyz) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
+  ctx->dsm_had_h2d = false;
+  int st = dsm_run(ctx, d_xyz, n, interpolation_radius, center_easting, center_northing);
+  ctx->dsm_timed = (st == AMB_OK);
+  return st;
+}
+
+int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpolation_radius,
+                    double center_easting, double center_northing) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;
+  if (!xyz) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, ctx->points.reserve(n * 3 * sizeof(double)));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->points.ptr, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
+  ctx->dsm_had_h2d = true;
+  int st = dsm_run(ctx, ctx->points.as<double>(), n, interpolation_radius, center_easting, center_northing);
+  ctx->dsm_timed = (st == AMB_OK);
+  if (st != AMB_OK) return st;
+  return finish_flags(ctx, 1, AMB_ERR_COINCIDENT_POINT);
+}
+
+int amb_dsm_enable_debug(amb_ctx* ctx, int enable) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->dsm_debug = enable != 0;
+  if (!enable) ctx->dsm_debug_valid = false;
+  return AMB_OK;
+}
+
+int amb_dsm_download_debug(amb_ctx* ctx, int32_t* neighbour_count, int8_t* threshold_index) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->dsm_debug_valid) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t cells = ctx->slab_cells();
+  if (neighbour_count)
+    AMB_CUDA(ctx, cudaMemcpyAsync(neighbour_count, ctx->dbg_count.ptr, cells * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  if (threshold_index)
+    AMB_CUDA(ctx, cudaMemcpyAsync(threshold_index, ctx->dbg_level.ptr, cells, cudaMemcpyDeviceToHost, ctx->stream));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMB_OK;
+}
+
+int amb_dsm_thresholds(int32_t interpolation_radius, double* thresholds, int32_t capacity) {
+  if (interpolation_radius < 1 || !thresholds || capacity <= 0) return AMB_ERR_INVALID_ARGUMENT;
+  const std::vector<double> thr = dsm_thresholds(interpolation_radius);
+  const int n = static_cast<int>(std::min<size_t>(thr.size(), static_cast<size_t>(capacity)));
+  for (int k = 0; k < n; ++k) thresholds[k] = thr[k];
+  return n;
+}
+
+// ---- Ortho ----
+int amb_ortho_process_device(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B,
+                             const uint8_t* const* d_images, size_t n, int32_t channels, size_t row_step,
+                             int32_t colored_ortho) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_BEGIN], ctx->stream));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_H2D_END], ctx->stream));
+  ctx->ortho_had_h2d = false;
+  int st = ortho_run(ctx, camera, T_G_B, d_images, n, channels, row_step, colored_ortho);
+  if (st == AMB_OK) AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_END], ctx->stream));
+  ctx->ortho_timed = (st == AMB_OK);
+  return st;
+}
+
+int amb_ortho_process(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* images,
+                      size_t n, int32_t channels, size_t row_step, int32_t colored_ortho) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;
+  if (!camera || !T_G_B || !images) return AMB_ERR_INVALID_ARGUMENT;
+  if (camera->width <= 0 || camera->height <= 0) return AMB_ERR_SIZE_MISMATCH;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t frame_bytes = static_cast<size_t>(camera->height) * row_step;
+  const size_t frame_pitch = (frame_bytes + 255) & ~static_cast<size_t>(255);
+  AMB_CUDA(ctx, ctx->frames.reserve(frame_pitch * n));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_BEGIN], ctx->stream));
+  std::vector<const uint8_t*> d_ptrs(n);
+  for (size_t f = 0; f < n; ++f) {
+    if (!images[f]) return AMB_ERR_INVALID_ARGUMENT;
+    uint8_t* dst = ctx->frames.as<uint8_t>() + f * frame_pitch;
+    AMB_CUDA(ctx, cudaMemcpyAsync(dst, images[f], frame_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_ptrs[f] = dst;
+  }
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_H2D_END], ctx->stream));
+  ctx->ortho_had_h2d = true;
+  int st = ortho_run(ctx, camera, T_G_B, d_ptrs.data(), n, channels, row_step, colored_ortho);
+  if (st != AMB_OK) return st;
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_END], ctx->stream));
+  ctx->ortho_timed = true;
+  return finish_flags(ctx, 8, AMB_ERR_CHECK_FAILED);
+}
+
+int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->ortho_brute_force = brute_force != 0;
+  return AMB_OK;
+}
+
+// ---- measurement ----
+int amb_get_timings(amb_ctx* ctx, amb_timings* out) {
+  if (!ctx || !out) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memset(out, 0, sizeof(*out));
+  auto ms = [&](int a, int b) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->events[a], ctx->events[b]) != cudaSuccess) {
+      cudaGetLastError();
+      t = 0.f;
+    }
+    return t;
+  };
+  if (ctx->dsm_timed) {
+    out->dsm_h2d_ms = ctx->dsm_had_h2d ? ms(EV_DSM_BEGIN, EV_DSM_H2D_END) : 0.f;
+    out->dsm_bin_ms = ms(EV_DSM_H2D_END, EV_DSM_BIN_END);
+    out->dsm_gather_ms = ms(EV_DSM_BIN_END, EV_DSM_GATHER_END);
+    out->dsm_fill_ms = ms(EV_DSM_GATHER_END, EV_DSM_FILL_END);
+    out->dsm_total_ms = ms(EV_DSM_BEGIN, EV_DSM_FILL_END);
+    out->dsm_kernel_launches = ctx->dsm_launches;
+    unsigned int c[4] = {0, 0, 0, 0};
+    if (ctx->counters.ptr) {
+      AMB_CUDA(ctx, cudaMemcpy(c, ctx->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
+    }
+    out->dsm_cells_empty = c[0];
+    out->dsm_points_binned = c[2];
+  }
+  if (ctx->ortho_timed) {
+    out->ortho_h2d_ms = ctx->ortho_had_h2d ? ms(EV_ORTHO_BEGIN, EV_ORTHO_H2D_END) : 0.f;
+    out->ortho_kernel_ms = ms(EV_ORTHO_H2D_END, EV_ORTHO_END);
+    out->ortho_total_ms = ms(EV_ORTHO_BEGIN, EV_ORTHO_END);
+    out->ortho_kernel_launches = ctx->ortho_launches;
+  }
+  return AMB_OK;
+}
+
+int amb_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return AMB_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return AMB_ERR_CUDA;
+  }
+  return AMB_OK;
+}
+
+int amb_host_free(void* ptr) {
+  if (!ptr) return AMB_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return AMB_ERR_CUDA;
+  }
+  return AMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// amb_context.h — internal state behind the C ABI (include/aerial_mapper_b200.h).  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aerial_mapper_b200.h"
+
+namespace amb {
+
+constexpr int kNumSMsB200 = 148;
+
+// A grow-only device buffer: process() is called repeatedly on the same context (incremental mapping,
+// main-ortho-backward-grid-incremental.cc:143-163), so scratch is allocated once and kept.
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t want) {
+    if (want <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    // round up so that slowly growing inputs do not reallocate every call
+    size_t alloc = (want + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc(&ptr, alloc);
+    if (e == cudaSuccess) bytes = alloc;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(ptr);
+  }
+};
+
+enum EventId {
+  EV_DSM_BEGIN = 0,
+  EV_DSM_H2D_END,
+  EV_DSM_BIN_END,
+  EV_DSM_GATHER_END,
+  EV_DSM_FILL_END,
+  EV_ORTHO_BEGIN,
+  EV_ORTHO_H2D_END,
+  EV_ORTHO_END,
+  EV_COUNT
+};
+
+}  // namespace amb
+
+struct amb_ctx {
+  amb_geometry geom;
+  int device = 0;
+  int32_t col_begin = 0, col_end = 0;  // owned column stripe
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D staging overlapped with compute
+  cudaEvent_t events[amb::EV_COUNT] = {};
+  cudaEvent_t copy_done[2] = {};
+  bool dsm_timed = false, ortho_timed = false, dsm_had_h2d = false, ortho_had_h2d = false;
+  int32_t dsm_launches = 0, ortho_launches = 0;
+  std::string last_error;
+
+  float* layers[AMB_NUM_LAYERS] = {};
+
+  // DSM scratch
+  amb::DeviceBuffer points;       // device copy of the caller's xyz (host entry point)
+  amb::DeviceBuffer records;      // bin-sorted 32-byte point records
+  amb::DeviceBuffer bin_starts;   // uint32 G[nb + 2]
+  amb::DeviceBuffer block_sums;   // scan spine
+  amb::DeviceBuffer empty_cells;  // uint32 list of cells that need the expanding-radius pass
+  amb::DeviceBuffer counters;     // small: [0] empty count, [1] error flag, [2] binned points (2 x uint32)
+  amb::DeviceBuffer dbg_count;    // int32 per slab cell
+  amb::DeviceBuffer dbg_level;    // int8 per slab cell
+  bool dsm_debug = false;
+  bool dsm_debug_valid = false;
+  int64_t last_points_binned = 0, last_cells_empty = 0;
+
+  // Ortho scratch
+  amb::DeviceBuffer frames;       // device copies of the caller's frames (host entry point)
+  amb::DeviceBuffer frame_table;  // per-frame device image pointers
+  amb::DeviceBuffer frame_cull;   // per-frame camera centre + optical axis (tile cull test)
+  bool ortho_brute_force = false;
+
+  size_t slab_cells() const { return static_cast<size_t>(geom.rows) * static_cast<size_t>(col_end - col_begin); }
+};
+
+namespace amb {
+
+inline int fail(amb_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) {
+    ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  }
+  return AMB_ERR_CUDA;
+}
+
+#define AMB_CUDA(ctx, call)                                   \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return amb::fail(ctx, e__, #call); \
+  } while (0)
+
+int ensure_layer(amb_ctx* ctx, int layer);
+
+// Implemented in dsm_kernels.cu / ortho_kernels.cu
+int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius, double center_easting,
+            double center_northing);
+int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
+              size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
+std::vector<double> dsm_thresholds(int32_t interpolation_radius);
+
+}  // namespace amb

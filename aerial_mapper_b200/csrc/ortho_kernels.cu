@@ -1,0 +1,435 @@
+// ortho_kernels.cu — grid-based orthomosaic back-projection on sm_100a.
+//
+// Replaces ortho::OrthoBackwardGrid::process (reference aerial_mapper_ortho/src/ortho-backward-grid.cc:223-239)
+// and its cell loop (:128-221).  Per cell: landmark = (cell centre, (double)elevation); for every frame in
+// ascending index: transform into the camera (:157-158), project with the distortion model (:159-161), test
+// visibility (:164-171), alpha = asin(|z|/norm) (:173-177); a frame replaces the cell's state iff
+// alpha > (double)elevation_angle (float32 layer, :180); the winner's nearest-neighbour texel is written
+// (:186-206).  Winner-takes-all with a float-rounded running maximum — a sequential recurrence per cell, so it
+// is evaluated by one thread per cell in frame order; frames are the inner loop, cells the parallel axis.
+//
+// What makes it fast: the reference projects every cell into every frame.  Here a 32x8 cell tile first discards
+// the frames whose view cone cannot contain any of its cells (a provably conservative test, see
+// compute_view_cone), keeps the survivors as an ascending index list in shared memory, and every thread walks
+// that list reading the per-frame constants (R_C_G, t, camera centre) from __constant__ memory — all threads of
+// a block read the same frame at the same time, i.e. a constant-cache broadcast.
+#include <cfloat>
+#include <cmath>
+
+#include "amb_context.h"
+
+namespace amb {
+namespace {
+
+constexpr int kMaxFramesPerLaunch = 512;
+constexpr int OTI = 32;  // tile extent along i (rows; contiguous in memory)
+constexpr int OTJ = 8;   // tile extent along j
+constexpr int kOrthoThreads = OTI * OTJ;
+
+struct FrameConst {
+  double m[9];  // R_C_G (row-major): X_c = m * X + t
+  double t[3];  // -R_C_G * t_G_C
+};
+static_assert(sizeof(FrameConst) * kMaxFramesPerLaunch <= 64 * 1024, "constant memory budget");
+
+__constant__ FrameConst c_frames[kMaxFramesPerLaunch];
+
+struct OrthoArgs {
+  const float* elevation;
+  float* elevation_angle;
+  float* observation_index;
+  float* out_layer;               // `ortho` (gray) or `colored_ortho` (packed colour bits)
+  const uint8_t* const* images;   // device array: frame -> device raster
+  const double* cull_data;        // device array [n_frames][6]: camera centre, optical axis (map frame)
+  unsigned int* error_flag;
+  size_t row_step;
+  int n_frames, frame_base;       // frames in this launch; index of its first frame within the process() call
+  int rows, cols_slab, col_begin;
+  int width, height, channels, colored;
+  int dist_type;
+  int do_cull;                    // 0: brute force over all frames
+  int cone;                       // 1: view-cone test active (else only "behind the camera")
+  double base_x, base_y, res;
+  double fu, fv, cu, cv;
+  double d0, d1, d2, d3;
+  double cos_c, sin_c;            // half-angle of the conservative view cone
+};
+
+__device__ __forceinline__ bool project(const OrthoArgs& a, double x, double y, double z, double* kx, double* ky) {
+  // aslam::PinholeCamera::project3: rz = 1/z; (u,v) = (x,y)*rz; distort; k = f*u + c.  Returns the reference's
+  // keypoint_visible predicate (ortho-backward-grid.cc:164-171): inside the raster and z > 1e-10
+  // (POINT_BEHIND_CAMERA is z < 0, PROJECTION_INVALID is 0 <= z <= 1e-10; both rejected).
+  const double rz = 1.0 / z;
+  double u = x * rz;
+  double v = y * rz;
+  if (a.dist_type == AMB_DIST_RADTAN) {
+    const double mx2 = u * u, my2 = v * v, mxy = u * v;
+    const double rho2 = mx2 + my2;
+    const double rad = a.d0 * rho2 + a.d1 * rho2 * rho2;
+    const double un = u + (u * rad + 2.0 * a.d2 * mxy + a.d3 * (rho2 + 2.0 * mx2));
+    const double vn = v + (v * rad + 2.0 * a.d3 * mxy + a.d2 * (rho2 + 2.0 * my2));
+    u = un;
+    v = vn;
+  } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
+    const double r = sqrt(u * u + v * v);
+    if (r > 1e-8) {
+      const double th = atan(r);
+      const double th2 = th * th, th4 = th2 * th2, th6 = th4 * th2, th8 = th4 * th4;
+      const double thd = th * (1.0 + a.d0 * th2 + a.d1 * th4 + a.d2 * th6 + a.d3 * th8);
+      const double s = thd / r;
+      u *= s;
+      v *= s;
+    }
+  }
+  *kx = a.fu * u + a.cu;
+  *ky = a.fv * v + a.cv;
+  return (*kx >= 0.0) && (*ky >= 0.0) && (*kx < static_cast<double>(a.width)) &&
+         (*ky < static_cast<double>(a.height)) && (z > 1e-10);
+}
+
+__global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_constant__ OrthoArgs a) {
+  __shared__ unsigned short s_list[kMaxFramesPerLaunch];
+  __shared__ float s_red[2][kOrthoThreads / 32];
+  __shared__ int s_warp_cnt[kOrthoThreads / 32];
+  __shared__ int s_total;
+
+  const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
+  const int tiles_i = (a.rows + OTI - 1) / OTI;
+  const int i0 = (blockIdx.x % tiles_i) * OTI;
+  const int j0 = (blockIdx.x / tiles_i) * OTJ;
+  const int i = i0 + ti, jl = j0 + tj;
+  const bool in_range = (i < a.rows) && (jl < a.cols_slab);
+  const size_t cell = static_cast<size_t>(jl) * a.rows + i;
+
+  float elev = __int_as_float(0x7fc00000);
+  if (in_range) elev = a.elevation[cell];
+  const bool valid = in_range && !isnan(elev);  // NaN elevation: every comparison is false, cell untouched
+
+  // tile elevation range
+  float zmin = valid ? elev : FLT_MAX, zmax = valid ? elev : -FLT_MAX;
+  for (int o = 16; o > 0; o >>= 1) {
+    zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+    zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+  }
+  if (ti == 0) {
+    s_red[0][tj] = zmin;
+    s_red[1][tj] = zmax;
+  }
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  zmin = s_red[0][0];
+  zmax = s_red[1][0];
+#pragma unroll
+  for (int w = 1; w < kOrthoThreads / 32; ++w) {
+    zmin = fminf(zmin, s_red[0][w]);
+    zmax = fmaxf(zmax, s_red[1][w]);
+  }
+  if (zmin > zmax) return;  // no cell of this tile has an elevation
+
+  // bounding sphere of the tile's landmarks (cell centres x elevation range)
+  const int i1 = min(i0 + OTI, a.rows) - 1, j1 = min(j0 + OTJ, a.cols_slab) - 1;
+  const double x_hi = a.base_x - a.res * i0, x_lo = a.base_x - a.res * i1;
+  const double y_hi = a.base_y - a.res * (a.col_begin + j0), y_lo = a.base_y - a.res * (a.col_begin + j1);
+  const double sx = 0.5 * (x_hi + x_lo), sy = 0.5 * (y_hi + y_lo);
+  const double sz = 0.5 * (static_cast<double>(zmin) + static_cast<double>(zmax));
+  const double ex = 0.5 * (x_hi - x_lo), ey = 0.5 * (y_hi - y_lo);
+  const double ez = 0.5 * (static_cast<double>(zmax) - static_cast<double>(zmin));
+  const double rho = sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9) + 1e-6;
+
+  // ordered list of the frames that may see the tile
+  for (int f0 = 0; f0 < a.n_frames; f0 += kOrthoThreads) {
+    const int f = f0 + threadIdx.x;
+    bool keep = f < a.n_frames;
+    if (keep && a.do_cull) {
+      // per-thread frame index: read from global memory (a divergent __constant__ index would serialise)
+      const double* cf = a.cull_data + 6 * static_cast<size_t>(f);
+      const double dx = sx - __ldg(cf + 0), dy = sy - __ldg(cf + 1), dz = sz - __ldg(cf + 2);
+      const double zp = dx * __ldg(cf + 3) + dy * __ldg(cf + 4) + dz * __ldg(cf + 5);  // along the optical axis
+      const double dd = dx * dx + dy * dy + dz * dz;
+      if (zp + rho <= 0.0) {
+        keep = false;  // whole sphere behind the camera plane: z_c <= 0 for every landmark
+      } else if (a.cone) {
+        const double perp = sqrt(fmax(dd - zp * zp, 0.0));
+        // distance from the sphere centre to the solid cone {angle to axis <= theta_c} is at least
+        // perp*cos(theta_c) - zp*sin(theta_c)
+        if (perp * a.cos_c - zp * a.sin_c > rho + 1e-9 * (perp + fabs(zp))) keep = false;
+      }
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, keep);
+    if (ti == 0) s_warp_cnt[tj] = __popc(m);
+    __syncthreads();
+    int before = s_total;
+    for (int w = 0; w < tj; ++w) before += s_warp_cnt[w];
+    if (keep) s_list[before + __popc(m & ((1u << ti) - 1u))] = static_cast<unsigned short>(f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = s_total;
+      for (int w = 0; w < kOrthoThreads / 32; ++w) t += s_warp_cnt[w];
+      s_total = t;
+    }
+    __syncthreads();
+  }
+  const int n_list = s_total;
+  if (!valid || n_list == 0) return;
+
+  const double X = __dadd_rn(a.base_x, __dmul_rn(a.res, -static_cast<double>(i)));
+  const double Y = __dadd_rn(a.base_y, __dmul_rn(a.res, -static_cast<double>(a.col_begin + jl)));
+  const double Z = static_cast<double>(elev);
+  float best = a.elevation_angle[cell];
+  int best_f = -1;
+  double best_kx = 0.0, best_ky = 0.0;
+  bool check_failed = false;
+
+  for (int l = 0; l < n_list; ++l) {
+    const int f = s_list[l];
+    const FrameConst& fc = c_frames[f];
+    const double xc = fc.m[0] * X + fc.m[1] * Y + fc.m[2] * Z + fc.t[0];
+    const double yc = fc.m[3] * X + fc.m[4] * Y + fc.m[5] * Z + fc.t[1];
+    const double zc = fc.m[6] * X + fc.m[7] * Y + fc.m[8] * Z + fc.t[2];
+    if (!(zc > 1e-10)) continue;
+    double kx, ky;
+    if (!project(a, xc, yc, zc, &kx, &ky)) continue;
+    const double norm = sqrt(xc * xc + yc * yc + zc * zc);
+    const double alpha = asin(fabs(zc) / norm);
+    if (!(alpha > 0.0)) check_failed = true;  // reference: CHECK(alpha > 0.0), :178
+    if (alpha > static_cast<double>(best)) {  // :180 — double against the float32 layer value
+      best = static_cast<float>(alpha);       // :181
+      best_f = f;
+      best_kx = kx;
+      best_ky = ky;
+    }
+  }
+  if (check_failed) atomicExch(a.error_flag, 1u);
+  if (best_f < 0) return;
+
+  a.elevation_angle[cell] = best;
+  a.observation_index[cell] = static_cast<float>(a.frame_base + best_f);  // :182
+  // :183 num_observations += num_observations — 0 stays 0, layer untouched.
+  // :186-193 — round half away from zero, clamp to the last row / column.
+  const int py = min(static_cast<int>(round(best_ky)), a.height - 1);
+  const int px = min(static_cast<int>(round(best_kx)), a.width - 1);
+  const uint8_t* img = a.images[best_f];
+  const uint8_t* texel = img + static_cast<size_t>(py) * a.row_step + static_cast<size_t>(px) * a.channels;
+  if (a.colored) {
+    // :194-202 + grid_map::colorVectorToValue: cv::Vec3b is (B,G,R); the packed value is 0x00RRGGBB moved as
+    // raw bits (int(float(c/255.0)*255.0f) == c for every byte c; tests/test_oracle_ortho.py checks all 256).
+    const unsigned int b = __ldg(texel), g = __ldg(texel + 1), r = __ldg(texel + 2);
+    a.out_layer[cell] = __uint_as_float((r << 16) | (g << 8) | b);
+  } else {
+    a.out_layer[cell] = static_cast<float>(__ldg(texel));  // :203-206
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side: pose algebra (kindr::minimal::QuatTransformation / Eigen quaternion formulas, restated)
+struct Quat {
+  double w, x, y, z;
+};
+struct V3 {
+  double x, y, z;
+};
+inline Quat qmul(const Quat& a, const Quat& b) {
+  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+inline V3 cross(const V3& a, const V3& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+inline V3 qrot(const Quat& q, const V3& v) {
+  const V3 qv = {q.x, q.y, q.z};
+  V3 uv = cross(qv, v);
+  uv.x += uv.x;
+  uv.y += uv.y;
+  uv.z += uv.z;
+  const V3 c = cross(qv, uv);
+  return {(v.x + q.w * uv.x) + c.x, (v.y + q.w * uv.y) + c.y, (v.z + q.w * uv.z) + c.z};
+}
+
+// Conservative view cone of camera 0: the smallest half-angle theta_c (about the optical axis) such that NO ray
+// further off-axis can project inside the raster, for the given distortion model.  A point at normalised radius
+// r = tan(theta) is imaged at D(u,v); it is inside the raster only if |D| <= Dmax (the farthest raster corner
+// from the principal point, in normalised units).  We lower-bound |D| on intervals of r (or theta) with a
+// Lipschitz bound on the radial polynomial and scan from far off-axis inwards; the first interval that might
+// reach |D| <= Dmax ends the scan.  If even the outermost interval might (fold-back of a non-monotone
+// polynomial, or pure tangential distortion), the cone is disabled and only "behind the camera" culls.
+bool compute_view_cone(const amb_camera& cam, double* cos_c, double* sin_c) {
+  const double ax = std::max(cam.cu, cam.width - cam.cu) / std::fabs(cam.fu);
+  const double ay = std::max(cam.cv, cam.height - cam.cv) / std::fabs(cam.fv);
+  const double dmax = std::sqrt(ax * ax + ay * ay) * (1.0 + 1e-9);
+  double rc = -1.0;  // tan(theta_c)
+  const double* k = cam.dist;
+  if (cam.dist_type == AMB_DIST_NONE || (cam.dist_type == AMB_DIST_RADTAN && k[0] == 0 && k[1] == 0 &&
+                                          k[2] == 0 && k[3] == 0)) {
+    rc = dmax;
+  } else if (cam.dist_type == AMB_DIST_RADTAN) {
+    const double k1 = k[0], k2 = k[1], T = std::fabs(k[2]) + std::fabs(k[3]);
+    // |D| >= r*|1 + k1 r^2 + k2 r^4| - 4 T r^2   (|tangential| <= 4 T r^2)
+    const double rmax = 1.0e3;
+    // tail r >= rmax: the leading radial term must dominate and keep growing
+    bool tail_ok = false;
+    {
+      const double r = rmax;
+      if (k2 != 0.0) {
+        const double low = r * (std::fabs(k2) * r * r * r * r - std::fabs(k1) * r * r - 1.0) - 4.0 * T * r * r;
+        const double slope_ok = 5.0 * std::fabs(k2) * r * r * r * r >= 2.0 * (3.0 * std::fabs(k1) * r * r + 1.0 + 8.0 * T * r);
+        tail_ok = slope_ok && low > dmax;
+      } else if (k1 != 0.0) {
+        const double low = r * (std::fabs(k1) * r * r - 1.0) - 4.0 * T * r * r;
+        const double slope_ok = 3.0 * std::fabs(k1) * r * r >= 2.0 * (1.0 + 8.0 * T * r);
+        tail_ok = slope_ok && low > dmax;
+      }
+    }
+    if (!tail_ok) return false;
+    double b = rmax;
+    rc = 0.0;
+    while (b > 1e-4) {
+      const double a = b / 1.0005;
+      const double poly_a = std::fabs(1.0 + k1 * a * a + k2 * a * a * a * a);
+      const double lip = std::fabs(2.0 * k1 * b) + std::fabs(4.0 * k2 * b * b * b);
+      const double low = a * std::max(0.0, poly_a - lip * (b - a)) - 4.0 * T * b * b;
+      if (low <= dmax) {
+        rc = b;
+        break;
+      }
+      b = a;
+    }
+    if (rc >= rmax) return false;
+    if (rc == 0.0) rc = 1e-4;
+  } else if (cam.dist_type == AMB_DIST_EQUIDISTANT) {
+    // |D| = |theta * (1 + k1 th^2 + k2 th^4 + k3 th^6 + k4 th^8)|, theta = atan(r) in [0, pi/2)
+    const double half_pi = 1.5707963267948966;
+    const double step = 1e-4;
+    double b = half_pi + step;
+    double thc = -1.0;
+    bool first = true;
+    while (b > 0.0) {
+      const double a = std::max(0.0, b - step);
+      const double a2 = a * a;
+      const double poly_a = std::fabs(1.0 + k[0] * a2 + k[1] * a2 * a2 + k[2] * a2 * a2 * a2 + k[3] * a2 * a2 * a2 * a2);
+      const double lip = std::fabs(2 * k[0] * b) + std::fabs(4 * k[1] * b * b * b) + std::fabs(6 * k[2] * std::pow(b, 5)) +
+                         std::fabs(8 * k[3] * std::pow(b, 7));
+      const double low = a * std::max(0.0, poly_a - lip * (b - a));
+      if (low <= dmax) {
+        if (first) return false;
+        thc = b;
+        break;
+      }
+      first = false;
+      b = a;
+    }
+    if (thc < 0.0) thc = step;
+    if (thc >= half_pi - 1e-3) return false;
+    rc = std::tan(thc);
+  } else {
+    return false;
+  }
+  rc *= (1.0 + 1e-6);
+  const double h = std::sqrt(1.0 + rc * rc);
+  *cos_c = 1.0 / h;
+  *sin_c = rc / h;
+  return true;
+}
+
+}  // namespace
+
+int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
+              size_t n, int32_t channels, size_t row_step, int32_t colored_ortho) {
+  if (n == 0) return AMB_ERR_EMPTY;  // CHECK(!T_G_Bs.empty()), ortho-backward-grid.cc:225
+  if (!camera || !T_G_B || !d_images) return AMB_ERR_INVALID_ARGUMENT;
+  if (colored_ortho ? channels != 3 : channels != 1) return AMB_ERR_SIZE_MISMATCH;
+  if (camera->width <= 0 || camera->height <= 0 || row_step < static_cast<size_t>(camera->width) * channels)
+    return AMB_ERR_SIZE_MISMATCH;
+  if (camera->dist_type < AMB_DIST_NONE || camera->dist_type > AMB_DIST_EQUIDISTANT) return AMB_ERR_UNSUPPORTED;
+  const int out_layer = colored_ortho ? AMB_LAYER_COLORED_ORTHO : AMB_LAYER_ORTHO;
+  const int need[4] = {AMB_LAYER_ELEVATION, AMB_LAYER_ELEVATION_ANGLE, AMB_LAYER_OBSERVATION_INDEX, out_layer};
+  for (int l : need) {
+    const int st = ensure_layer(ctx, l);
+    if (st != AMB_OK) return st;
+  }
+  const amb_geometry& g = ctx->geom;
+  cudaStream_t s = ctx->stream;
+
+  // T_G_C = T_G_B * T_C_B^-1 (ortho-backward-grid.cc:230-233), then the per-frame constants of
+  // X_c = T_G_C^-1 . X = R_C_G X - R_C_G t_G_C.
+  const Quat q_C_B = {camera->q_C_B[0], camera->q_C_B[1], camera->q_C_B[2], camera->q_C_B[3]};
+  const Quat q_B_C = {q_C_B.w, -q_C_B.x, -q_C_B.y, -q_C_B.z};
+  const V3 t_C_B = {camera->t_C_B[0], camera->t_C_B[1], camera->t_C_B[2]};
+  const V3 r_tmp = qrot(q_B_C, t_C_B);
+  const V3 t_B_C = {-r_tmp.x, -r_tmp.y, -r_tmp.z};
+  std::vector<FrameConst> fcs(n);
+  std::vector<double> cull(6 * n);
+  for (size_t f = 0; f < n; ++f) {
+    const double* p = T_G_B + 7 * f;
+    const Quat q_G_B = {p[3], p[4], p[5], p[6]};
+    const V3 t_G_B = {p[0], p[1], p[2]};
+    const Quat q = qmul(q_G_B, q_B_C);
+    const V3 rt = qrot(q_G_B, t_B_C);
+    const V3 t = {t_G_B.x + rt.x, t_G_B.y + rt.y, t_G_B.z + rt.z};
+    // rows of R_C_G = images of the map axes under q^-1, i.e. columns of R_G_C transposed
+    const Quat qi = {q.w, -q.x, -q.y, -q.z};
+    const V3 ex = qrot(qi, V3{1, 0, 0}), ey = qrot(qi, V3{0, 1, 0}), ez = qrot(qi, V3{0, 0, 1});
+    FrameConst& fc = fcs[f];
+    fc.m[0] = ex.x; fc.m[1] = ey.x; fc.m[2] = ez.x;
+    fc.m[3] = ex.y; fc.m[4] = ey.y; fc.m[5] = ez.y;
+    fc.m[6] = ex.z; fc.m[7] = ey.z; fc.m[8] = ez.z;
+    const V3 ti = qrot(qi, t);
+    fc.t[0] = -ti.x; fc.t[1] = -ti.y; fc.t[2] = -ti.z;
+    double* cf = &cull[6 * f];
+    cf[0] = t.x; cf[1] = t.y; cf[2] = t.z;
+    cf[3] = fc.m[6]; cf[4] = fc.m[7]; cf[5] = fc.m[8];
+  }
+
+  AMB_CUDA(ctx, ctx->frame_table.reserve(n * sizeof(uint8_t*)));
+  AMB_CUDA(ctx, ctx->counters.reserve(64));
+  unsigned int* counters = ctx->counters.as<unsigned int>();
+  AMB_CUDA(ctx, cudaMemsetAsync(counters + 8, 0, 4, s));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, d_images, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
+  AMB_CUDA(ctx, ctx->frame_cull.reserve(6 * n * sizeof(double)));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull.data(), 6 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+
+  OrthoArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.elevation = ctx->layers[AMB_LAYER_ELEVATION];
+  a.elevation_angle = ctx->layers[AMB_LAYER_ELEVATION_ANGLE];
+  a.observation_index = ctx->layers[AMB_LAYER_OBSERVATION_INDEX];
+  a.out_layer = ctx->layers[out_layer];
+  a.error_flag = counters + 8;
+  a.row_step = row_step;
+  a.rows = g.rows;
+  a.cols_slab = ctx->col_end - ctx->col_begin;
+  a.col_begin = ctx->col_begin;
+  a.width = camera->width;
+  a.height = camera->height;
+  a.channels = channels;
+  a.colored = colored_ortho ? 1 : 0;
+  a.dist_type = camera->dist_type;
+  a.base_x = g.pos_x + (0.5 * g.length_x - 0.5 * g.resolution);
+  a.base_y = g.pos_y + (0.5 * g.length_y - 0.5 * g.resolution);
+  a.res = g.resolution;
+  a.fu = camera->fu; a.fv = camera->fv; a.cu = camera->cu; a.cv = camera->cv;
+  a.d0 = camera->dist[0]; a.d1 = camera->dist[1]; a.d2 = camera->dist[2]; a.d3 = camera->dist[3];
+  a.do_cull = ctx->ortho_brute_force ? 0 : 1;
+  double cc = 0.0, sc = 1.0;
+  a.cone = compute_view_cone(*camera, &cc, &sc) ? 1 : 0;
+  a.cos_c = cc;
+  a.sin_c = sc;
+
+  const int tiles_i = (a.rows + OTI - 1) / OTI, tiles_j = (a.cols_slab + OTJ - 1) / OTJ;
+  ctx->ortho_launches = 0;
+  for (size_t f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {  // ascending chunks keep the frame order
+    const size_t nf = std::min<size_t>(kMaxFramesPerLaunch, n - f0);
+    // The staging vector must outlive the async copy; pageable source -> the copy is staged before returning.
+    AMB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_frames, fcs.data() + f0, nf * sizeof(FrameConst), 0,
+                                          cudaMemcpyHostToDevice, s));
+    a.n_frames = static_cast<int>(nf);
+    a.frame_base = static_cast<int>(f0);
+    a.images = ctx->frame_table.as<const uint8_t*>() + f0;
+    a.cull_data = ctx->frame_cull.as<double>() + 6 * f0;
+    ortho_kernel<<<tiles_i * tiles_j, kOrthoThreads, 0, s>>>(a);
+    ctx->ortho_launches += 1;
+  }
+  AMB_CUDA(ctx, cudaGetLastError());
+  return AMB_OK;
+}
+
+}  // namespace amb

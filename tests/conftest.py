@@ -1,0 +1,38 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with `pytest -m gpu` on the B200 box)")
+
+
+def _gpu_count():
+    try:
+        import aerial_mapper_b200 as amb
+        n = amb.lib().amb_device_count()
+        return max(n, 0)
+    except Exception:
+        return 0
+
+
+@pytest.fixture(scope="session")
+def gpu_count():
+    return _gpu_count()
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` tests must FAIL (not skip) when the CUDA library is missing on a GPU box; without any device they
+    # are skipped so that an accidental plain `pytest` on the CPU container stays green.
+    n = None
+    for item in items:
+        if "gpu" in item.keywords:
+            if n is None:
+                n = _gpu_count()
+            if n == 0 and not os.environ.get("AMB_REQUIRE_GPU"):
+                item.add_marker(pytest.mark.skip(reason="no CUDA device visible"))
