@@ -51,8 +51,10 @@ class GridMap(object):
     download().
     """
 
-    def __init__(self, layer_names=LAYER_NAMES):
+    def __init__(self, layer_names=LAYER_NAMES, pinned=False):
         self.layer_names = tuple(layer_names)
+        self.pinned = bool(pinned)  # allocate the host layers in page-locked memory (full-rate PCIe copies)
+        self._pinned_ptrs = []
         self.geometry = None
         self.layers = {}
         self.frame_id = ""
@@ -70,10 +72,29 @@ class GridMap(object):
         check(lib().amb_geometry_init(float(length[0]), float(length[1]), float(resolution), float(position[0]),
                                       float(position[1]), C.byref(g)))
         self.geometry = g
-        nan = np.float32(np.nan)
-        self.layers = {name: np.full((g.rows, g.cols), nan, dtype=np.float32, order="F")
-                       for name in self.layer_names}
+        self._free_pinned()
+        self.layers = {}
+        for name in self.layer_names:
+            a = self._alloc_layer(g.rows, g.cols)
+            a[...] = np.float32(np.nan)  # grid_map::GridMap::setGeometry -> clearAll()
+            self.layers[name] = a
         self._release()
+
+    def _alloc_layer(self, rows, cols):
+        if not self.pinned:
+            return np.empty((rows, cols), dtype=np.float32, order="F")
+        p = C.c_void_p()
+        nbytes = rows * cols * 4
+        check(lib().amb_host_alloc(C.byref(p), nbytes))
+        self._pinned_ptrs.append(p)
+        buf = (C.c_float * (rows * cols)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape((rows, cols), order="F")
+
+    def _free_pinned(self):
+        self.layers = {}
+        for p in self._pinned_ptrs:
+            lib().amb_host_free(p)
+        self._pinned_ptrs = []
 
     def getSize(self):
         return (self.geometry.rows, self.geometry.cols)
@@ -158,6 +179,7 @@ class GridMap(object):
     def __del__(self):
         try:
             self._release()
+            self._free_pinned()
         except Exception:
             pass
 
@@ -165,22 +187,22 @@ class GridMap(object):
 class AerialGridMap(object):
     """grid_map::AerialGridMap (aerial-mapper-grid-map.cc:23-49) without the ROS publisher."""
 
-    def __init__(self, settings):
+    def __init__(self, settings, pinned=False, layer_names=LAYER_NAMES):
         self.settings_ = settings
-        self.map_ = GridMap(LAYER_NAMES)  # :25-28
+        self.map_ = GridMap(layer_names, pinned=pinned)  # :25-28
         self.map_.setFrameId("world")
         self.map_.setGeometry((settings.delta_easting, settings.delta_northing), settings.resolution,
                               (settings.center_easting, settings.center_northing))  # :30-33
-        m = self.map_
-        m["ortho"] = 255.0               # :40-48
-        m["elevation"] = np.nan
-        m["elevation_angle"] = 0.0
-        m["elevation_angle_first_view"] = np.nan
-        m["num_observations"] = 0.0
-        m["observation_index"] = np.nan
-        m["observation_index_first"] = np.nan
-        m["delta"] = np.nan
-        m["colored_ortho"] = np.nan
+        self.reset()
+
+    INITIAL_VALUES = {"ortho": 255.0, "elevation": np.nan, "elevation_angle": 0.0,
+                      "elevation_angle_first_view": np.nan, "num_observations": 0.0, "observation_index": np.nan,
+                      "observation_index_first": np.nan, "delta": np.nan, "colored_ortho": np.nan}
+
+    def reset(self):
+        """The setConstant() calls of AerialGridMap::initialize (aerial-mapper-grid-map.cc:40-48)."""
+        for name in self.map_.layer_names:
+            self.map_[name] = self.INITIAL_VALUES[name]
 
     def getMutable(self):
         return self.map_

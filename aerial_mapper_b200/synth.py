@@ -103,16 +103,27 @@ IMAGE_B = (241, 151, 37)
 IMAGE_C = (17, 29, 43)
 
 
+_BASE_CACHE = {}
+
+
+def _image_base(width, height, c):
+    """(A[c]*u + B[c]*v + ((u*v) >> 3)) & 0xFF as uint8 [H, W]; frame k adds C[c]*k modulo 256."""
+    key = (width, height, c)
+    if key not in _BASE_CACHE:
+        u = np.arange(width, dtype=np.int64)[None, :]
+        v = np.arange(height, dtype=np.int64)[:, None]
+        _BASE_CACHE.clear() if len(_BASE_CACHE) > 6 else None
+        _BASE_CACHE[key] = ((IMAGE_A[c] * u + IMAGE_B[c] * v + ((u * v) >> 3)) & 0xFF).astype(np.uint8)
+    return _BASE_CACHE[key]
+
+
 def procedural_image(k, width, height, channels=1):
     """Frame k as uint8 [H, W] (gray) or [H, W, 3] (B, G, R byte order like cv::Mat CV_8UC3)."""
-    u = np.arange(width, dtype=np.int64)[None, :]
-    v = np.arange(height, dtype=np.int64)[:, None]
-    uv = (u * v) >> 3
     if channels == 1:
-        return ((IMAGE_A[0] * u + IMAGE_B[0] * v + IMAGE_C[0] * k + uv) & 0xFF).astype(np.uint8)
+        return _image_base(width, height, 0) + np.uint8((IMAGE_C[0] * k) & 0xFF)  # uint8 add wraps modulo 256
     img = np.empty((height, width, 3), dtype=np.uint8)
     for c in range(3):
-        img[:, :, c] = (IMAGE_A[c] * u + IMAGE_B[c] * v + IMAGE_C[c] * k + uv) & 0xFF
+        img[:, :, c] = _image_base(width, height, c) + np.uint8((IMAGE_C[c] * k) & 0xFF)
     return img
 
 
@@ -125,12 +136,13 @@ def procedural_images_torch(n, width, height, channels, device):
     uv = (u * v) >> 3
     shape = (n, height, width) if channels == 1 else (n, height, width, 3)
     out = torch.empty(shape, dtype=torch.uint8, device=device)
+    bases = [((IMAGE_A[c] * u + IMAGE_B[c] * v + uv) & 0xFF).to(torch.uint8) for c in range(channels)]
     for k in range(n):
         if channels == 1:
-            out[k] = ((IMAGE_A[0] * u + IMAGE_B[0] * v + IMAGE_C[0] * k + uv) & 0xFF).to(torch.uint8)
+            out[k] = bases[0] + ((IMAGE_C[0] * k) & 0xFF)  # uint8 add wraps modulo 256
         else:
             for c in range(3):
-                out[k, :, :, c] = ((IMAGE_A[c] * u + IMAGE_B[c] * v + IMAGE_C[c] * k + uv) & 0xFF).to(torch.uint8)
+                out[k, :, :, c] = bases[c] + ((IMAGE_C[c] * k) & 0xFF)
     return out
 
 

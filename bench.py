@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py — grid cells/s of the DSM + orthomosaic hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step is one pass of the hot path over one batch of synthetic input: reset the layers to AerialGridMap's initial
+values, dsm::Dsm::process over the point cloud, ortho::OrthoBackwardGrid::process over the frames (so every step
+does the whole job; nothing is cached between steps).
+
+  value  whole-job cells/s with the inputs already resident in HBM (kernel path, CUDA events / barrier + sync)
+  e2e    the same metric through the public host API (aerial_mapper_b200.Dsm / OrthoBackwardGrid .process with HOST
+         buffers): pinned host -> device copies of points, frames and the layers the path reads, device -> host
+         copies of the layers it writes, all inside the timed region
+  roofline / cpu_baseline   see DESIGN.md §Measurement
+
+--impl reference times the reference's CPU algorithm (oracle/_ref: its vendored nanoflann compiled verbatim +
+the restated cell loops, parFor over all host threads) on a bounded sample of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): the map is sharded by contiguous column stripes; points
+and frames are resident on every rank ("broadcast once", outside the timed region); each rank computes its stripe;
+one NCCL all-gather of the finished stripes per step inside the timed region.  Strong scaling: the job is fixed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # BASELINE.json configs[3] at one GPU = the configuration north_star quotes the >=1e8 cells/s target on:
+    # 50 M points + 250 frames of 4000x3000 -> 10000x10000 @ 0.25 m (joint DSM + ortho).
+    "joint_10k": dict(rows=10000, cols=10000, res=0.25, n_points=50_000_000, lines=10, per_line=25, agl=400.0,
+                      cam_scale=1.0, cpu_stripe_cols=400),
+    # small variants for tests of this script
+    "joint_1k": dict(rows=1000, cols=1000, res=0.25, n_points=500_000, lines=4, per_line=5, agl=100.0,
+                     cam_scale=0.25, cpu_stripe_cols=40),
+    "joint_256": dict(rows=256, cols=256, res=0.5, n_points=60_000, lines=2, per_line=3, agl=60.0,
+                      cam_scale=0.1, cpu_stripe_cols=32),
+}
+
+DSM_BYTES_PER_POINT = 24  # read each point once
+DSM_BYTES_PER_CELL = 4    # write each elevation once
+ORTHO_BYTES_PER_CELL_GRAY = 21
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="joint_10k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+def device_point_cloud(torch, n, half_x, half_y, device, seed=2):
+    """config C2 points generated in HBM (same distribution as synth.point_cloud; torch RNG, seeded)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    xyz = torch.empty((n, 3), dtype=torch.float64, device=device)
+    xyz[:, 0] = (torch.rand(n, generator=g, device=device, dtype=torch.float64) * 2 - 1) * half_x
+    xyz[:, 1] = (torch.rand(n, generator=g, device=device, dtype=torch.float64) * 2 - 1) * half_y
+    xyz[:, 2] = (100.0 + 10.0 * torch.sin(0.01 * xyz[:, 0]) * torch.cos(0.01 * xyz[:, 1]) +
+                 0.05 * torch.randn(n, generator=g, device=device, dtype=torch.float64))
+    return xyz
+
+
+def cuda_array(torch, ptr, shape_f32, device):
+    """Wrap a device pointer owned by the C library as a torch float32 tensor (NCCL plumbing)."""
+    class _W(object):
+        pass
+    w = _W()
+    n = int(np.prod(shape_f32))
+    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                  "strides": None}
+    return torch.as_tensor(w, device=device)
+
+
+def run_ours(args):
+    import torch
+    import aerial_mapper_b200 as amb
+    from aerial_mapper_b200 import synth
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun --nproc-per-node %d" %
+                             (args.gpus, args.gpus))
+    if amb.lib().amb_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    wl = WORKLOADS[args.workload]
+    rows, cols, res = wl["rows"], wl["cols"], wl["res"]
+    half_x, half_y = rows * res / 2, cols * res / 2
+    cells = rows * cols
+    camd = synth.scaled_camera(wl["cam_scale"]) if wl["cam_scale"] != 1.0 else dict(synth.C3_CAMERA)
+    poses = synth.lawnmower_poses(wl["lines"], wl["per_line"], half_x, half_y, wl["agl"], seed=4)
+    n_frames = len(poses)
+    W, H = camd["width"], camd["height"]
+
+    # column stripe of this rank
+    c0 = (cols * rank) // world
+    c1 = (cols * (rank + 1)) // world
+
+    # ---- synthetic inputs, generated in HBM ----
+    xyz_d = device_point_cloud(torch, wl["n_points"], half_x, half_y, device)
+    imgs_d = synth.procedural_images_torch(n_frames, W, H, 1, device)
+    torch.cuda.synchronize()
+    n_points = xyz_d.shape[0]
+    img_ptrs = [imgs_d[k].data_ptr() for k in range(n_frames)]
+
+    layer_names = ("ortho", "elevation", "elevation_angle", "observation_index")
+    settings = amb.GridMapSettings(0.0, 0.0, rows * res, cols * res, res)
+    agm = amb.AerialGridMap(settings, pinned=True, layer_names=layer_names)
+    gm = agm.getMutable()
+    gm.to_device(local_rank, col_range=(c0, c1), names=layer_names)
+    ctx = gm.context()
+    dsm = amb.Dsm(amb.DsmSettings(), gm)
+    ortho = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=False), gm)
+
+    gather_out = None
+    slab_tensors = None
+    if world > 1:
+        slab = rows * (c1 - c0)
+        slab_tensors = []
+        for name in layer_names:
+            p = C.c_void_p()
+            amb.check(amb.lib().amb_layer_device_ptr(ctx, amb.LAYER_ID[name], C.byref(p)))
+            slab_tensors.append(cuda_array(torch, p.value, (slab,), device))
+        assert cols % world == 0, "equal stripes required for the single all-gather"
+        gather_in = torch.empty(len(layer_names) * slab, dtype=torch.float32, device=device)
+        gather_out = torch.empty(world * len(layer_names) * slab, dtype=torch.float32, device=device)
+
+    def step_resident():
+        amb.check(amb.lib().amb_init_layers(ctx), ctx)
+        dsm.process_device(xyz_d.data_ptr(), n_points, gm)
+        ortho.process_device(poses, img_ptrs, W, gm)
+        gm.sync()
+        if world > 1:
+            slab = rows * (c1 - c0)
+            for k, t in enumerate(slab_tensors):
+                gather_in[k * slab:(k + 1) * slab].copy_(t)
+            dist.all_gather_into_tensor(gather_out, gather_in)  # the one collective of the step
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gather_ms, bin_ms, fill_ms, ortho_ms, launches = [], [], [], [], 0
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+        tm = gm.timings()  # CUDA events on the library's stream; the stream is already idle here
+        gather_ms.append(tm["dsm_gather_ms"])
+        bin_ms.append(tm["dsm_bin_ms"])
+        fill_ms.append(tm["dsm_fill_ms"])
+        ortho_ms.append(tm["ortho_kernel_ms"])
+        launches += tm["dsm_kernel_launches"] + tm["ortho_kernel_launches"] + len(layer_names)
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_total = max(ev0.elapsed_time(ev1), 1e-6)
+    # torch's events sit on torch's stream while the library runs on its own; the host-side sync inside every step
+    # makes both clocks agree — take the larger of the two to be safe.
+    ms_total = max(ms_total, wall_ms)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = cells / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through the public API ----
+    e2e = None
+    if not args.no_e2e:
+        xyz_h = torch.empty((n_points, 3), dtype=torch.float64, pin_memory=True)
+        xyz_h.copy_(xyz_d)
+        imgs_h = torch.empty((n_frames, H, W), dtype=torch.uint8, pin_memory=True)
+        imgs_h.copy_(imgs_d)
+        torch.cuda.synchronize()
+        xyz_np = xyz_h.numpy()
+        img_np = [imgs_h[k].numpy() for k in range(n_frames)]
+        gm_h = amb.AerialGridMap(settings, pinned=True, layer_names=layer_names)
+        gmh = gm_h.getMutable()
+        gmh.context(local_rank, (c0, c1))
+        dsm_h = amb.Dsm(amb.DsmSettings(), gmh)
+        ortho_h = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=False), gmh)
+        slab_bytes = rows * (c1 - c0) * 4
+
+        def step_e2e():
+            gm_h.reset()                       # host-side AerialGridMap::initialize values
+            dsm_h.process(xyz_np, gmh)         # H2D points + elevation, D2H elevation
+            ortho_h.process(poses, img_np, gmh)  # H2D frames + 4 layers, D2H 3 layers
+
+        e2e_steps = max(1, min(args.steps, 3))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = n_points * 24 + n_frames * H * W + 5 * slab_bytes
+        d2h = 4 * slab_bytes
+        e2e = {"value": cells / float(te.item()), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
+               "api": "aerial_mapper_b200.Dsm.process + OrthoBackwardGrid.process on host numpy buffers (pinned)"}
+        del gm_h, gmh
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_hbm()
+    stripe_cells = rows * (c1 - c0)
+    alg_bytes = DSM_BYTES_PER_POINT * n_points + DSM_BYTES_PER_CELL * stripe_cells
+    g_ms = float(np.mean(gather_ms))
+    achieved = alg_bytes / (g_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "dsm_gather_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": g_ms,
+                "stage_ms": {"dsm_bin": float(np.mean(bin_ms)), "dsm_gather": g_ms,
+                             "dsm_fill": float(np.mean(fill_ms)), "ortho": float(np.mean(ortho_ms))}}
+    out = {"metric": "grid cells/sec (DSM+ortho)", "value": value, "unit": "cells/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res), "points": int(n_points),
+                      "frames": "%dx %dx%d gray" % (n_frames, W, H), "interpolation_radius": 1,
+                      "sharding": "column stripes x%d, 1 all-gather/step" % world if world > 1 else "single GPU",
+                      "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W) / 1e9)},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if e2e is not None:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_reference(args, steps=1, warmup=0)["cpu_baseline"]
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference(args, steps, warmup):
+    """The reference's CPU algorithm on a bounded sample of the workload: a contiguous column stripe of cells with
+    the points that can reach it and ALL frames (the reference projects every cell into every frame)."""
+    from aerial_mapper_b200 import synth
+    from oracle import pyoracle as po
+
+    wl = WORKLOADS[args.workload]
+    rows, cols, res = wl["rows"], wl["cols"], wl["res"]
+    half_x, half_y = rows * res / 2, cols * res / 2
+    camd = synth.scaled_camera(wl["cam_scale"]) if wl["cam_scale"] != 1.0 else dict(synth.C3_CAMERA)
+    poses = synth.lawnmower_poses(wl["lines"], wl["per_line"], half_x, half_y, wl["agl"], seed=4)
+    n_frames = len(poses)
+    sc = min(wl["cpu_stripe_cols"], cols)
+    j0 = (cols - sc) // 2
+    geom = po.make_geometry(rows, cols, res)
+    # points of the stripe + 3 m (largest retry threshold reaches 2.6 m), same density / terrain as the workload
+    y_hi = half_y - res * j0 + 3.0
+    y_lo = half_y - res * (j0 + sc) - 3.0
+    n_sample = int(round(wl["n_points"] * (y_hi - y_lo) / (2 * half_y)))
+    rng = np.random.Generator(np.random.PCG64(2))
+    xyz = np.empty((n_sample, 3))
+    xyz[:, 0] = rng.uniform(-half_x, half_x, n_sample)
+    xyz[:, 1] = rng.uniform(y_lo, y_hi, n_sample)
+    xyz[:, 2] = synth.terrain(xyz[:, 0], xyz[:, 1]) + rng.normal(0, 0.05, n_sample)
+    imgs = [synth.procedural_image(k, camd["width"], camd["height"]) for k in range(n_frames)]
+    cam = po.make_camera(**camd)
+    use_ref = po.have_ref()
+    threads = po.hardware_concurrency()
+    k0, k1 = rows * j0, rows * (j0 + sc)
+    sample_cells = k1 - k0
+
+    def one():
+        layers = {"elevation": np.full((rows, cols), np.nan, np.float32, order="F"),
+                  "elevation_angle": np.zeros((rows, cols), np.float32, order="F"),
+                  "observation_index": np.full((rows, cols), np.nan, np.float32, order="F"),
+                  "ortho": np.full((rows, cols), 255.0, np.float32, order="F")}
+        t0 = time.perf_counter()
+        st, _, _, sec = po.dsm_process(geom, layers["elevation"], xyz, num_threads=0, cell_range=(k0, k1),
+                                       use_ref=use_ref)
+        assert st == 0, st
+        st, osec = po.ortho_process(geom, layers, cam, poses, imgs, num_threads=0, cell_range=(k0, k1))
+        assert st == 0, st
+        return time.perf_counter() - t0, sec, osec
+
+    for _ in range(warmup):
+        one()
+    times, dsm_secs, ortho_secs = [], [], []
+    for _ in range(max(1, steps)):
+        t, sec, osec = one()
+        times.append(t)
+        dsm_secs.append(sec.tolist())
+        ortho_secs.append(osec)
+    t_step = float(np.mean(times))
+    value = sample_cells / t_step
+    kind = "port"
+    sample = ("%d-column stripe (%d cells of %d) at the map centre, %d points within stripe+3 m, all %d frames; "
+              "DSM = %s; ortho = restated loop; parFor over %d threads; kd-tree build %.2fs + cell loop %.2fs, "
+              "ortho loop %.2fs" % (sc, sample_cells, rows * cols, n_sample, n_frames,
+                                    "reference's vendored nanoflann.hpp compiled verbatim + restated cell loop "
+                                    "(oracle/_ref)" if use_ref else "dependency-free restatement (oracle/)",
+                                    threads, dsm_secs[-1][0], dsm_secs[-1][1], ortho_secs[-1]))
+    base = {"value": value, "unit": "cells/s", "cores": threads, "kind": kind, "sample": sample}
+    return {"cpu_baseline": base, "ms_per_step": t_step * 1e3, "value": value,
+            "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res),
+                       "points": int(wl["n_points"]), "frames": "%dx %dx%d gray" % (n_frames, camd["width"],
+                                                                                  camd["height"]),
+                       "interpolation_radius": 1}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    r = cpu_reference(args, steps=args.steps, warmup=min(args.warmup, 1))
+    out = {"impl": "reference", "metric": "grid cells/sec (DSM+ortho)", "value": r["value"], "unit": "cells/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": r["config"], "cpu_baseline": r["cpu_baseline"],
+           "e2e": {"value": r["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -70,6 +70,36 @@ def ortho_case(rows, cols, res, lines, per_line, agl, scale, colored, dist_type=
     print(json.dumps(out), flush=True)
 
 
+def ortho_big(rows, cols, res, lines, per_line, agl, colored=False, brute=False, reps=3):
+    import torch
+    half_x, half_y = rows * res / 2, cols * res / 2
+    camd = dict(synth.C3_CAMERA)
+    poses = synth.lawnmower_poses(lines, per_line, half_x, half_y, agl, 4)
+    n = len(poses)
+    ch = 3 if colored else 1
+    dev = torch.device("cuda:0")
+    imgs = synth.procedural_images_torch(n, camd["width"], camd["height"], ch, dev)
+    torch.cuda.synchronize()
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+    gm.layers["elevation"][...] = synth.analytic_elevation(rows, cols, res)
+    gm.to_device(0)
+    o = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=colored), gm)
+    o.brute_force = brute
+    ptrs = [imgs[k].data_ptr() for k in range(n)]
+    for r in range(reps):
+        amb.lib().amb_init_layers(gm.context())
+        gm.upload(("elevation",))
+        o.process_device(poses, ptrs, camd["width"] * ch, gm)
+        gm.sync()
+        tim = gm.timings()
+        print(json.dumps(dict(case="ortho_big %dx%d@%g frames=%d colored=%d brute=%d rep=%d" % (
+            rows, cols, res, n, colored, brute, r), **{k: v for k, v in tim.items() if k.startswith("ortho")})),
+            flush=True)
+    gm.download(("observation_index",))
+    oi = gm["observation_index"]
+    print(json.dumps(dict(covered=int((~np.isnan(oi)).sum()), cells=rows * cols)), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "small"
     if which in ("small", "all"):
@@ -86,3 +116,8 @@ if __name__ == "__main__":
     if which in ("big", "all"):
         dsm_case(4000, 4000, 0.25, 8000000, 2, big=True)
         dsm_case(10000, 10000, 0.25, 50000000, 2, big=True)
+        dsm_case(10000, 10000, 0.25, 50000000, 2, big=True)
+    if which in ("obig", "all"):
+        ortho_big(8000, 8000, 0.5, 10, 25, 600.0)
+        ortho_big(8000, 8000, 0.5, 10, 25, 600.0, colored=True, reps=2)
+        ortho_big(2000, 2000, 0.5, 10, 25, 600.0, brute=True, reps=1)
