@@ -4,10 +4,10 @@ orthomosaic back-projection) behind the reference's own class API.  See DESIGN.m
 The compute lives in libaerial_mapper_b200.so (hand-written sm_100a CUDA, C ABI in include/aerial_mapper_b200.h).
 """
 from ._lib import (AMB_OK, AmbError, Camera, Geometry, LAYER_ID, LAYER_NAMES, DIST_EQUIDISTANT, DIST_NONE,
-                   DIST_RADTAN, LIB_PATH, build, lib)
+                   DIST_RADTAN, LIB_PATH, build, check, lib)
 from .api import (AerialGridMap, Dsm, DsmSettings, GridMap, GridMapSettings, HOT_LAYERS, NCamera,
                   OrthoBackwardGrid, OrthoSettings, dsm_thresholds)
 
 __all__ = ["AMB_OK", "AmbError", "Camera", "Geometry", "LAYER_ID", "LAYER_NAMES", "DIST_EQUIDISTANT", "DIST_NONE",
-           "DIST_RADTAN", "LIB_PATH", "build", "lib", "AerialGridMap", "Dsm", "DsmSettings", "GridMap",
+           "DIST_RADTAN", "LIB_PATH", "build", "check", "lib", "AerialGridMap", "Dsm", "DsmSettings", "GridMap",
            "GridMapSettings", "HOT_LAYERS", "NCamera", "OrthoBackwardGrid", "OrthoSettings", "dsm_thresholds"]
