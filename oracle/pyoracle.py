@@ -152,6 +152,8 @@ def ortho_process(geom, layers, camera, T_G_B, images, colored=False, num_thread
     T = np.ascontiguousarray(T_G_B, dtype=np.float64).reshape(-1, 7)
     n = T.shape[0]
     assert len(images) == n
+    if n == 0:
+        return -1, 0.0  # AMB_ERR_EMPTY: CHECK(!T_G_Bs.empty()), ortho-backward-grid.cc:225
     imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
     channels = 3 if colored else 1
     h, w = imgs[0].shape[:2]

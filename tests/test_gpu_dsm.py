@@ -1,0 +1,235 @@
+"""GPU parity of the DSM path: the CUDA library through the C ABI (aerial_mapper_b200.Dsm = dsm::Dsm mirror)
+against the CPU oracle on the same seeded inputs, the golden fixture, and size-independent properties at scale.
+
+Bars: neighbour counts, retry-threshold indices and the NaN mask are integer-exact; elevation within 1e-6
+relative (north_star allows 1e-4) — and in fact expected bit-identical up to double summation order."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, ulp_diff
+import aerial_mapper_b200 as amb
+from aerial_mapper_b200 import synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def gpu_dsm(rows, cols, res, xyz, radius=1, ce=0.0, cn=0.0, pos=(0.0, 0.0), elevation=None, col_range=None):
+    gm = amb.AerialGridMap(amb.GridMapSettings(pos[0], pos[1], rows * res, cols * res, res)).getMutable()
+    assert gm.getSize() == (rows, cols)
+    if elevation is not None:
+        gm["elevation"] = elevation
+    if col_range is not None:
+        gm.context(0, col_range)
+    d = amb.Dsm(amb.DsmSettings(interpolation_radius=radius, center_easting=ce, center_northing=cn), gm)
+    d.debug = True
+    d.process(xyz, gm)
+    return gm, d.last_debug
+
+
+def oracle_dsm(rows, cols, res, xyz, radius=1, ce=0.0, cn=0.0, pos=(0.0, 0.0), elevation=None):
+    g = po.make_geometry(rows, cols, res, pos[0], pos[1])
+    e = np.full((rows, cols), np.nan, np.float32, order="F")
+    if elevation is not None:
+        e[...] = elevation
+    st, cnt, lvl, _ = po.dsm_process(g, e, xyz, radius=radius, center_easting=ce, center_northing=cn, debug=True)
+    assert st == 0
+    return e, cnt, lvl
+
+
+def assert_parity(gm, dbg, e, cnt, lvl):
+    gc, gl = dbg
+    ge = gm["elevation"]
+    assert np.array_equal(gl, lvl), "retry-threshold index differs in %d cells" % int((gl != lvl).sum())
+    touched = lvl >= 0
+    assert np.array_equal(gc[touched], cnt[touched]), "neighbour count differs"
+    assert (gc[~touched] == 0).all()
+    assert np.array_equal(np.isnan(ge), np.isnan(e))
+    ok = ~np.isnan(e)
+    assert np.allclose(ge[ok], e[ok], rtol=REL, atol=0.0)
+    assert ulp_diff(ge, e).max() <= 1
+
+
+CASES = [
+    # rows, cols, res, n, seed, holes, radius
+    (256, 256, 1.0, 100000, 1, 0, 1),      # BASELINE config C1
+    (300, 200, 0.25, 40000, 5, 6, 1),      # holes -> every retry level and permanent NaN
+    (100, 130, 0.5, 20000, 6, 0, 2),       # radius 2 m^2
+    (97, 61, 0.4, 9000, 8, 2, 1),          # tile-unaligned sizes, odd resolution
+    (33, 500, 1.0, 30000, 9, 0, 3),
+    (64, 64, 0.1, 3000, 10, 0, 1),         # window half-width 10 cells
+    (40, 40, 2.0, 20000, 11, 0, 1),        # cells larger than the search radius
+    (50, 50, 1.0, 12000, 12, 0, 8),        # radius > 7: exactly one retry, no growth
+]
+
+
+@pytest.mark.parametrize("rows,cols,res,n,seed,holes,radius", CASES)
+def test_matches_oracle(rows, cols, res, n, seed, holes, radius):
+    xyz = synth.point_cloud(n, rows * res / 2 + 2.0, cols * res / 2 + 2.0, seed, holes=holes,
+                            hole_sides=(rows * res / 30, rows * res / 6))
+    gm, dbg = gpu_dsm(rows, cols, res, xyz, radius)
+    assert_parity(gm, dbg, *oracle_dsm(rows, cols, res, xyz, radius))
+
+
+def test_golden_fixture():
+    z = np.load(os.path.join(GOLDEN, "dsm_96x80.npz"))
+    rows, cols, res = int(z["rows"]), int(z["cols"]), float(z["res"])
+    gm, (gc, gl) = gpu_dsm(rows, cols, res, z["xyz"])
+    assert np.array_equal(gl, z["threshold_index"])
+    t = gl >= 0
+    assert np.array_equal(gc[t], z["neighbour_count"][t])
+    assert np.array_equal(np.isnan(gm["elevation"]), np.isnan(z["elevation"]))
+    assert ulp_diff(gm["elevation"], z["elevation"]).max() <= 1
+
+
+def test_map_offset_and_center_shift():
+    xyz = synth.point_cloud(15000, 30.0, 20.0, seed=14, center=(5000.0 + 7.0, -3000.0 - 2.0))
+    kw = dict(ce=-2.0, cn=7.0, pos=(5000.0, -3000.0))
+    gm, dbg = gpu_dsm(110, 70, 0.5, xyz, 1, **kw)
+    assert_parity(gm, dbg, *oracle_dsm(110, 70, 0.5, xyz, 1, **kw))
+
+
+def test_points_outside_the_map_still_count():
+    # the reference's kd-tree holds every point: points beyond the border contribute to edge cells
+    xyz = synth.point_cloud(8000, 30.0, 30.0, seed=15)   # map is 40 x 40 m, cloud 60 x 60 m
+    gm, dbg = gpu_dsm(40, 40, 1.0, xyz)
+    assert_parity(gm, dbg, *oracle_dsm(40, 40, 1.0, xyz))
+
+
+def test_repeated_process_keeps_untouched_cells():
+    a = synth.point_cloud(3000, 10.0, 20.0, seed=16, center=(-10.0, 0.0))
+    b = synth.point_cloud(3000, 10.0, 20.0, seed=17, center=(10.0, 0.0))
+    b[:, 2] += 40.0
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, 40.0, 40.0, 0.5)).getMutable()
+    d = amb.Dsm(amb.DsmSettings(), gm)
+    d.process(a, gm)
+    d.process(b, gm)
+    e, _, _ = oracle_dsm(80, 80, 0.5, a)
+    e, _, _ = oracle_dsm(80, 80, 0.5, b, elevation=e)
+    assert np.array_equal(np.isnan(gm["elevation"]), np.isnan(e))
+    assert ulp_diff(gm["elevation"], e).max() <= 1
+
+
+def test_resident_map_matches_host_mode():
+    xyz = synth.point_cloud(20000, 25.0, 25.0, seed=18, holes=3, hole_sides=(2.0, 8.0))
+    host, _ = gpu_dsm(100, 100, 0.5, xyz)
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, 50.0, 50.0, 0.5)).getMutable()
+    gm.to_device(0)
+    amb.Dsm(amb.DsmSettings(), gm).process(xyz, gm)
+    assert np.isnan(gm["elevation"]).all()          # host copy untouched until download
+    gm.download(("elevation",))
+    assert np.array_equal(gm["elevation"].view(np.uint32), host["elevation"].view(np.uint32))
+
+
+def test_run_to_run_and_stripe_determinism():
+    # the in-bin canonical order makes every output bit independent of atomic scheduling and of the striping
+    xyz = synth.point_cloud(60000, 40.0, 30.0, seed=19, holes=4, hole_sides=(2.0, 9.0))
+    full1, _ = gpu_dsm(160, 120, 0.5, xyz)
+    full2, _ = gpu_dsm(160, 120, 0.5, xyz)
+    assert np.array_equal(full1["elevation"].view(np.uint32), full2["elevation"].view(np.uint32))
+    for c0, c1 in [(0, 30), (30, 77), (77, 120)]:
+        part, (pc, pl) = gpu_dsm(160, 120, 0.5, xyz, col_range=(c0, c1))
+        assert np.array_equal(part["elevation"][:, c0:c1].view(np.uint32),
+                              full1["elevation"][:, c0:c1].view(np.uint32))
+        outside = np.ones(120, bool)
+        outside[c0:c1] = False
+        assert np.isnan(part["elevation"][:, outside]).all()   # other stripes are not this context's to write
+
+
+def test_errors():
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, 8.0, 8.0, 1.0)).getMutable()
+    d = amb.Dsm(amb.DsmSettings(), gm)
+    gm["elevation"] = 3.25
+    d.process(np.zeros((0, 3)), gm)                      # dsm.cc:189-192: warn + return
+    assert (gm["elevation"] == 3.25).all()
+    qx, qy = synth.grid_positions(8, 8, 1.0)
+    with pytest.raises(amb.AmbError) as ei:
+        d.process(np.array([[qx[2], qy[5], 1.0], [0.1, 0.2, 0.3]]), gm)
+    assert ei.value.status == -3                         # CHECK(distances[i] > 0.0), dsm.cc:165
+    with pytest.raises(amb.AmbError):
+        amb.Dsm(amb.DsmSettings(interpolation_radius=0), gm).process(np.ones((2, 3)), gm)
+
+
+def test_clustered_points_overflow_the_shared_memory_stage():
+    # 40k points inside one 32x32 tile: the tile falls back to reading its bins from global memory
+    rng = np.random.default_rng(20)
+    xyz = np.c_[rng.uniform(-3, 3, 40000), rng.uniform(-3, 3, 40000), rng.uniform(90, 110, 40000)]
+    gm, dbg = gpu_dsm(64, 64, 0.25, xyz)
+    assert_parity(gm, dbg, *oracle_dsm(64, 64, 0.25, xyz))
+
+
+# ---- size-independent properties at BASELINE-scale densities (no oracle needed) ----
+def test_property_constant_height_and_bounds_large():
+    import torch
+    rows = cols = 4000
+    res, n = 0.25, 8_000_000
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    xyz = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    xyz[:, 0] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * 500
+    xyz[:, 1] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * 500
+    xyz[:, 2] = 123.25
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res),
+                           layer_names=("elevation",)).getMutable()
+    gm.to_device(0, names=("elevation",))
+    d = amb.Dsm(amb.DsmSettings(), gm)
+    d.process_device(xyz.data_ptr(), n, gm)
+    gm.sync()
+    gm.download(("elevation",))
+    e = gm["elevation"]
+    assert not np.isnan(e).any()
+    assert (e == np.float32(123.25)).all()               # IDW of a constant is that constant
+    # bounds: IDW is a convex combination of the neighbours' heights
+    xyz[:, 2] = 100.0 + 10.0 * torch.sin(0.01 * xyz[:, 0]) * torch.cos(0.01 * xyz[:, 1])
+    d.process_device(xyz.data_ptr(), n, gm)
+    gm.sync()
+    gm.download(("elevation",))
+    e = gm["elevation"].astype(np.float64)
+    qx, qy = synth.grid_positions(rows, cols, res)
+    truth = synth.terrain(qx[:, None], qy[None, :])
+    assert np.abs(e - truth).max() < 0.11                # |grad| <= 0.1 per metre, neighbours within 1 m
+    assert e.min() >= 90.0 - 1e-3 and e.max() <= 110.0 + 1e-3
+
+
+def test_property_neighbour_checksum_large():
+    """Sum over cells of the neighbour count == sum over points of the number of cell centres within the radius,
+    the latter evaluated independently with torch (same un-fused double expression)."""
+    import torch
+    rows, cols, res, n = 3000, 2000, 0.25, 3_000_000
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    xyz = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    xyz[:, 0] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * (rows * res / 2 + 3)
+    xyz[:, 1] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * (cols * res / 2 + 3)
+    xyz[:, 2] = 50.0
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res),
+                           layer_names=("elevation",)).getMutable()
+    gm.to_device(0, names=("elevation",))
+    d = amb.Dsm(amb.DsmSettings(), gm)
+    d.debug = True
+    d.process_device(xyz.data_ptr(), n, gm)
+    gm.sync()
+    d._fetch_debug(gm)
+    cnt, lvl = d.last_debug
+    assert (lvl == 0).all()      # 8 points / m^2: the primary radius is never empty
+    base_x = 0.0 + (0.5 * rows * res - 0.5 * res)
+    base_y = 0.0 + (0.5 * cols * res - 0.5 * res)
+    px, py = xyz[:, 0], xyz[:, 1]
+    ci = torch.floor((base_x - px) / res + 0.5).to(torch.int64)
+    cj = torch.floor((base_y - py) / res + 0.5).to(torch.int64)
+    total = 0
+    for di in range(-5, 6):
+        for dj in range(-5, 6):
+            i, j = ci + di, cj + dj
+            inside = (i >= 0) & (i < rows) & (j >= 0) & (j < cols)
+            qx = base_x + res * (-(i.to(torch.float64)))
+            qy = base_y + res * (-(j.to(torch.float64)))
+            dx, dy = qx - px, qy - py
+            d2 = dx * dx + dy * dy
+            total += int(((d2 < 1.0) & inside).sum().item())
+    assert int(cnt.astype(np.int64).sum()) == total
