@@ -50,7 +50,9 @@ constexpr int kMaxHalfWidth = 128;  // cells; window half-width limit (sqrt(thre
 constexpr int TI = 32;              // tile extent along i (rows, the contiguous axis of the layer)
 constexpr int TJ = 32;              // tile extent along j
 constexpr int kGatherThreads = 256;
+constexpr int kStrip = 4;           // cells per thread in the gather kernel (adjacent along j)
 constexpr int kScanChunk = 4096;    // elements per block in the scan kernels (256 threads x 16)
+static_assert(TJ == kStrip * (kGatherThreads / 32), "one warp per strip row of the tile");
 
 struct PointRec {  // 32 bytes, one DRAM sector
   double x, y, z;
@@ -240,6 +242,17 @@ __global__ void __launch_bounds__(256) dsm_canon_kernel(const unsigned int* __re
   }
 }
 
+// Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~2^-23) + one cubic
+// correction step.  Replaces the two IEEE divisions per neighbour of the reference (heights/d2 and 1/d2) by one reciprocal
+// and one FMA; the IDW height changes by O(1e-16) relative, far inside the float32 layer's rounding.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);  // |e| <= 2^-23
+  const double t = fma(e, e, e);     // e + e^2: r*(1 + e + e^2) leaves a relative error e^3 <= 2^-69
+  return fma(r, t, r);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K4: tile gather
 struct GatherArgs {
@@ -254,6 +267,118 @@ struct GatherArgs {
   int tiles_i;
 };
 
+// Per-thread work of the gather kernel.  A thread owns kStrip cells with the same i and adjacent j; their windows
+// overlap in all but one bin row, so every staged point is loaded once, (qx - px)^2 is computed once, and only
+// the (qy - py)^2 + compare + accumulate part is per cell.  The thread walks the kStrip + 2W bin rows of its
+// strip as ONE flattened loop (lanes stay busy until their own candidates run out); per row, `srow` gives the
+// half-width of the widest window among the strip's cells and the mask of cells that row can reach.
+// Accumulation order per cell: bin rows ascending, points ascending inside a row == canonical bin order.
+template <bool STAGED, bool DEBUG>
+__device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherArgs& args, int off_srow, int off_sxy,
+                                             int off_spz, int i0, int j0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // addressed by byte offset: plain LDS, no generic ptr
+  const int W = plan.W;
+  const int NI = TI + 2 * W + 1;
+  const int ti = threadIdx.x & 31;
+  const int tq = threadIdx.x >> 5;  // warp index == strip index along j (warp-uniform)
+  const int i = i0 + ti;
+  const int jl0 = j0 + kStrip * tq;
+  const double qx = cell_x(plan, i);
+  const double thr0 = plan.thr0;
+  double qy[kStrip], num[kStrip], den[kStrip];
+  int cnt[kStrip];
+  unsigned int cellmask = 0;
+#pragma unroll
+  for (int m = 0; m < kStrip; ++m) {
+    qy[m] = cell_y(plan, plan.col_begin + jl0 + m);
+    num[m] = 0.0;
+    den[m] = 0.0;
+    cnt[m] = 0;
+    if (i < plan.rows && jl0 + m < plan.cols_slab) cellmask |= 1u << m;
+  }
+  const int n_rows = kStrip + 2 * W;
+  int r = -1;                                                    // row of the strip's window
+  int row_addr = ((kStrip * tq - 1) * NI + ti + W) * 4;          // byte offset of soff[row][ti + W]
+  unsigned int k = 0, e = 0;
+  if (cellmask) {
+    for (;;) {
+      if (k >= e) {
+        bool found = false;
+        while (r + 1 < n_rows) {
+          ++r;
+          row_addr += NI * 4;
+          const int info = *reinterpret_cast<const int*>(smem_raw + off_srow + 4 * r);  // (h << 8) | mask, or -1
+          if (info < 0) continue;
+          const int h4 = (info >> 8) * 4;
+          k = *reinterpret_cast<const unsigned int*>(smem_raw + row_addr - h4);
+          e = *reinterpret_cast<const unsigned int*>(smem_raw + row_addr + h4 + 4);
+          if (k < e) {
+            found = true;
+            break;
+          }
+        }
+        if (!found) break;
+      }
+      double2 p;
+      double pz;
+      if (STAGED) {
+        p = *reinterpret_cast<const double2*>(smem_raw + off_sxy + 16 * k);
+        pz = *reinterpret_cast<const double*>(smem_raw + off_spz + 8 * k);
+      } else {
+        p = __ldg(reinterpret_cast<const double2*>(args.rec + k));
+        pz = __ldg(reinterpret_cast<const double*>(args.rec + k) + 2);
+      }
+      const double dx = qx - p.x;
+      const double dx2 = __dmul_rn(dx, dx);
+      // Branch-free: every cell of the strip tests every staged point of the strip's rows.  A bin row that is out
+      // of a cell's reach (|dj| > W) holds only points with |dy| > sqrt(threshold), so it can never hit; a miss
+      // adds exactly 0 (w = 0: fma(z, 0, num) == num, den + 0 == den), so the sums are bit-identical to
+      // visiting only the reachable rows.
+#pragma unroll
+      for (int m = 0; m < kStrip; ++m) {
+        const double dy = qy[m] - p.y;
+        const double d2 = __dadd_rn(dx2, __dmul_rn(dy, dy));  // L2_Adaptor (nanoflann.hpp:325-328), un-contracted
+        const bool hit = d2 < thr0;                           // RadiusResultSet::addPoint (:156-158)
+        const double w = hit ? fast_rcp(d2) : 0.0;            // 1.0 / distances[i]         (dsm.cc:167)
+        num[m] = fma(pz, w, num[m]);                          // heights[i] / distances[i]  (dsm.cc:166), z * (1/d2)
+        den[m] += w;
+        if (DEBUG) cnt[m] += hit ? 1 : 0;
+      }
+      ++k;
+    }
+  }
+  bool coincident = false;
+#pragma unroll
+  for (int m = 0; m < kStrip; ++m) {
+    const bool valid = (cellmask >> m) & 1u;
+    const size_t cell = static_cast<size_t>(jl0 + m) * plan.rows + i;
+    const bool has = den[m] > 0.0 || den[m] != den[m];  // any hit adds a positive weight (NaN: coincident point)
+    if (valid) {
+      if (has) {
+        // d2 == 0 (a point exactly on the cell centre: reference CHECK(distances[i] > 0.0) aborts, dsm.cc:165)
+        // is the only way a weight becomes inf/NaN: any d2 > 0 is >= 1e-26 for metre-scale coordinates.
+        if (!(den[m] < DBL_MAX)) coincident = true;
+        args.elevation[cell] = __double2float_rn(__ddiv_rn(num[m], den[m]));  // dsm.cc:171-172
+      }
+      if (DEBUG) {
+        args.dbg_count[cell] = cnt[m];
+        args.dbg_level[cell] = has ? 0 : -1;
+      }
+    }
+    // cells the primary threshold left empty go to the retry pass: one atomic per warp
+    const bool is_empty = valid && !has;
+    const unsigned int mask = __ballot_sync(0xffffffffu, is_empty);
+    if (mask) {
+      const int leader = __ffs(mask) - 1;
+      unsigned int base = 0;
+      if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (is_empty) args.empty_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
+    }
+  }
+  if (coincident) atomicExch(&args.counters[1], 1u);
+}
+
 __global__ void __launch_bounds__(kGatherThreads)
     dsm_gather_kernel(const __grid_constant__ DsmPlan plan, const GatherArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -263,17 +388,31 @@ __global__ void __launch_bounds__(kGatherThreads)
   unsigned int* soff = reinterpret_cast<unsigned int*>(smem_raw);           // [NC][NI]
   unsigned int* colbase = soff + NC * NI;                                    // [NC + 1] local start of a column
   unsigned int* colg0 = colbase + (NC + 1);                                  // [NC] global start of a column
-  size_t off_bytes = (static_cast<size_t>(NC) * NI + 2 * NC + 1) * sizeof(unsigned int);
+  int* srow = reinterpret_cast<int*>(colg0 + NC);                            // [kStrip + 2W] strip row table
+  size_t off_bytes = (static_cast<size_t>(NC) * NI + 2 * NC + 1 + kStrip + 2 * W) * sizeof(unsigned int);
   off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
-  double* spx = reinterpret_cast<double*>(smem_raw + off_bytes);
-  double* spy = spx + args.capacity;
-  double* spz = spy + args.capacity;
+  double2* sxy = reinterpret_cast<double2*>(smem_raw + off_bytes);  // (x, y) of the staged points
+  double* spz = reinterpret_cast<double*>(sxy + args.capacity);
 
   const int tile_i = blockIdx.x % args.tiles_i;
   const int tile_j = blockIdx.x / args.tiles_i;
   const int i0 = tile_i * TI;
   const int j0 = tile_j * TJ;  // local column in the slab
 
+  for (int r = threadIdx.x; r < kStrip + 2 * W; r += kGatherThreads) {
+    // strip row r is bin row (first cell's j) - W + r; cell m of the strip sees it at dj = r - W - m
+    int hmax = -1, mask = 0;
+    for (int m = 0; m < kStrip; ++m) {
+      const int dj = r - W - m;
+      const int ad = dj < 0 ? -dj : dj;
+      const int h = ad <= W ? plan.hw[ad] : -1;
+      if (h >= 0) {
+        mask |= 1 << m;
+        hmax = max(hmax, h);
+      }
+    }
+    srow[r] = hmax < 0 ? -1 : ((hmax << 8) | mask);
+  }
   // 1. bin start offsets of the tile + apron (global values)
   for (int e = threadIdx.x; e < NC * NI; e += kGatherThreads) {
     const int jj = e / NI, ii = e - jj * NI;
@@ -325,11 +464,8 @@ __global__ void __launch_bounds__(kGatherThreads)
       const PointRec* src = args.rec + colg0[jj];
       const unsigned int dst = colbase[jj];
       for (unsigned int k = lane; k < len; k += 32) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(src + k));
-        const double z = __ldg(reinterpret_cast<const double*>(src + k) + 2);
-        spx[dst + k] = a.x;
-        spy[dst + k] = a.y;
-        spz[dst + k] = z;
+        sxy[dst + k] = __ldg(reinterpret_cast<const double2*>(src + k));
+        spz[dst + k] = __ldg(reinterpret_cast<const double*>(src + k) + 2);
       }
     }
   }
@@ -345,71 +481,20 @@ __global__ void __launch_bounds__(kGatherThreads)
   }
   __syncthreads();
 
-  // 4. per-cell gather
-  const int ti = threadIdx.x & 31;
-  const int tj0 = threadIdx.x >> 5;
-  const int i = i0 + ti;
-  const double qx = cell_x(plan, i);
-  const double thr0 = plan.thr0;
-#pragma unroll 1
-  for (int m = 0; m < TJ / (kGatherThreads / 32); ++m) {  // warp-uniform loop: a warp is one row of 32 cells
-    const int tj = tj0 + m * (kGatherThreads / 32);
-    const int jl = j0 + tj;
-    const bool valid = (i < plan.rows) && (jl < plan.cols_slab);
-    const size_t cell = static_cast<size_t>(jl) * plan.rows + i;
-    int cnt = 0;
-    if (valid) {
-      const double qy = cell_y(plan, plan.col_begin + jl);
-      double num = 0.0, den = 0.0;
-      bool coincident = false;
-      for (int dj = -W; dj <= W; ++dj) {
-        const int jj = tj + W + dj;
-        const int h = plan.hw[dj < 0 ? -dj : dj];
-        if (h < 0) continue;
-        const unsigned int a = soff[jj * NI + (ti + W - h)];
-        const unsigned int b = soff[jj * NI + (ti + W + h + 1)];
-        for (unsigned int k = a; k < b; ++k) {
-          double px, py;
-          if (staged) {
-            px = spx[k];
-            py = spy[k];
-          } else {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(args.rec + k));
-            px = v.x;
-            py = v.y;
-          }
-          const double dx = qx - px;
-          const double dy = qy - py;
-          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-          if (d2 < thr0) {
-            const double pz = staged ? spz[k] : __ldg(reinterpret_cast<const double*>(args.rec + k) + 2);
-            ++cnt;
-            if (d2 > 0.0) {
-              num += __ddiv_rn(pz, d2);  // heights[i] / distances[i]   (dsm.cc:166)
-              den += __drcp_rn(d2);      // 1.0 / distances[i]          (dsm.cc:167)
-            } else {
-              coincident = true;  // reference: CHECK(distances[i] > 0.0) aborts (dsm.cc:165)
-            }
-          }
-        }
-      }
-      if (coincident) atomicExch(&args.counters[1], 1u);
-      if (cnt > 0) args.elevation[cell] = __double2float_rn(__ddiv_rn(num, den));  // dsm.cc:171-172
-      if (args.dbg_count) {
-        args.dbg_count[cell] = cnt;
-        args.dbg_level[cell] = cnt > 0 ? 0 : -1;
-      }
+  // 4. per-cell gather: every thread owns a 1 x kStrip strip of cells (same i, adjacent j)
+  const int off_srow = static_cast<int>(reinterpret_cast<unsigned char*>(srow) - smem_raw);
+  const int off_sxy = static_cast<int>(off_bytes);
+  const int off_spz = off_sxy + 16 * args.capacity;
+  if (args.dbg_count) {  // tests: also record result_set.size() per cell
+    if (staged) {
+      gather_strip<true, true>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
+    } else {
+      gather_strip<false, true>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
     }
-    // cells the primary threshold left empty go to the retry pass: one atomic per warp
-    const bool is_empty = valid && cnt == 0;
-    const unsigned int mask = __ballot_sync(0xffffffffu, is_empty);
-    if (mask) {
-      const int leader = __ffs(mask) - 1;
-      unsigned int base = 0;
-      if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (is_empty) args.empty_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
-    }
+  } else if (staged) {
+    gather_strip<true, false>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
+  } else {
+    gather_strip<false, false>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
   }
 }
 
@@ -479,12 +564,10 @@ __global__ void __launch_bounds__(256) dsm_fill_kernel(const __grid_constant__ D
         if (d2 < thr) {
           const double pz = __ldg(reinterpret_cast<const double*>(args.rec + k) + 2);
           ++cnt;
-          if (d2 > 0.0) {
-            num += __ddiv_rn(pz, d2);
-            den += __drcp_rn(d2);
-          } else {
-            coincident = true;
-          }
+          const double w = fast_rcp(d2);
+          num = fma(pz, w, num);
+          den += w;
+          coincident |= !(d2 > 0.0);
         }
       }
     }
@@ -611,12 +694,18 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_r
   // gather
   const int W = plan.W;
   const int NC = TJ + 2 * W, NI = TI + 2 * W + 1;
-  size_t off_bytes = (static_cast<size_t>(NC) * NI + 2 * NC + 1) * sizeof(unsigned int);
+  size_t off_bytes = (static_cast<size_t>(NC) * NI + 2 * NC + 1 + kStrip + 2 * W) * sizeof(unsigned int);
   off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
-  // stage budget: aim at 4 resident blocks per SM (227 KB usable per SM)
-  const size_t budget = 56 * 1024;
+  // Stage size: 1.6x the expected number of points in a tile + apron under a uniform density (the tail of a
+  // Poisson count is far inside that; denser tiles fall back to global reads), clamped to [24 KB, 100 KB] so that
+  // several blocks stay resident per SM (227 KB usable).
   if (off_bytes + 3 * sizeof(double) * 64 > 200 * 1024) return AMB_ERR_UNSUPPORTED;
-  size_t smem = std::max(budget, off_bytes + 3 * sizeof(double) * 64);
+  const double avg_per_bin = static_cast<double>(n) / static_cast<double>(nb);
+  const double expect = avg_per_bin * static_cast<double>(NC) * static_cast<double>(NI - 1);
+  size_t smem = off_bytes + static_cast<size_t>(1.6 * expect + 64.0) * 3 * sizeof(double);
+  smem = std::min<size_t>(std::max<size_t>(smem, 24 * 1024), 100 * 1024);
+  smem = std::max(smem, off_bytes + 3 * sizeof(double) * 64);
+  smem = (smem + 1023) & ~static_cast<size_t>(1023);
   int capacity = static_cast<int>((smem - off_bytes) / (3 * sizeof(double)));
   GatherArgs ga;
   ga.G = G;
