@@ -132,7 +132,8 @@ void amb_destroy(amb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layers[l]) cudaFree(ctx->layers[l]);
-  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->records,   &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
+  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->records,   &ctx->point_order,
+                            &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
                           &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
                           &ctx->frame_cull};
   for (DeviceBuffer* b : bufs) b->release();

@@ -72,7 +72,8 @@ struct amb_ctx {
 
   // DSM scratch
   amb::DeviceBuffer points;       // device copy of the caller's xyz (host entry point)
-  amb::DeviceBuffer records;      // bin-sorted 32-byte point records
+  amb::DeviceBuffer records;      // bucket-sorted 32-byte point records
+  amb::DeviceBuffer point_order;  // uint32 per record: canonical (original-index) visiting order inside a bucket
   amb::DeviceBuffer bin_starts;   // uint32 G[nb + 2]
   amb::DeviceBuffer block_sums;   // scan spine
   amb::DeviceBuffer empty_cells;  // uint32 list of cells that need the expanding-radius pass

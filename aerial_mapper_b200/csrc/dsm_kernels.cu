@@ -5,25 +5,31 @@
 //     S   = { p : d2(p) < threshold }                 d2 = (qx-px)^2 + (qy-py)^2, un-contracted double
 //     h   = (sum_S z/d2) / (sum_S 1/d2)                elevation(i,j) = (float)h
 // with threshold = (double)interpolation_radius, or, when that set is empty, the first of the retry thresholds
-// lambda_k*radius (dsm.cc:133-144) that yields a non-empty set.  Nothing in that definition needs a tree: this
-// file bins the points to grid cells (one bin per cell plus an apron), and every cell gathers from the bins its
-// threshold can reach.
+// lambda_k*radius (dsm.cc:133-144) that yields a non-empty set.  Nothing in that definition needs a tree.
+//
+// Layout of the work
+//   HBM:   points are sorted into COARSE buckets of BxB grid cells (B a power of two chosen so that a bucket holds
+//          a few dozen points; 8x8 cells at the benchmark density).  The bucket histogram is small enough to live
+//          in L2 (1.6 M counters at 10^4 x 10^4 cells), so counting and scattering do not pay a DRAM
+//          read-modify-write per point, and a bucket's records are one contiguous ~1 KB run.
+//   SMEM:  a 32x32-cell tile loads the buckets overlapping its window (tile + apron), bins their points to CELLS with
+//          shared-memory atomics, orders every cell's points by original index, and gathers from there.
 //
 // Pipeline (all on the context's stream):
-//   K1 dsm_count_kernel      read AoS points, shift, bin id, atomicAdd histogram
-//   K2 scan_* (3 kernels)    inclusive scan of the histogram -> bin start offsets
-//   K3 dsm_scatter_kernel    write 32-byte records {x, y, z, original index} into bin order
-//   K3b dsm_canon_kernel     order the records of every multi-point bin by original index, so that the IDW
-//                            summation order (hence every output bit) is independent of atomic scheduling and
-//                            of how the map is striped across GPUs
-//   K4 dsm_gather_kernel     one 32x32 cell tile per block: the tile's bin ranges are staged through shared
-//                            memory (SoA doubles), each thread walks the bin rows of its cell's window
-//   K5 dsm_fill_kernel       cells with no neighbour inside the primary threshold: one warp per cell finds the
-//                            minimum d2 in the fallback window, picks the reference's threshold index, re-sums
+//   K1 dsm_count_kernel     AoS points -> bucket histogram (atomics resolve in L2)
+//   K2 scan_*               inclusive scan -> bucket start offsets
+//   K3 dsm_scatter_kernel   32-byte records {x, y, z, original index} into bucket order
+//   K3b dsm_bucket_order_kernel  one warp per bucket: visiting order of its records by original index (canonical
+//                           order: the IDW summation order — hence every output bit — is independent of atomic
+//                           scheduling and of how the map is striped across GPUs)
+//   K4 dsm_gather_kernel    one tile per block: bucket runs -> cell bins in shared memory -> every thread owns a
+//                           1x4 strip of cells and walks the strip's bin rows in one flattened, branch-free loop
+//   K5 dsm_cell_kernel      one warp per listed cell: cells whose primary ball is empty (expanding-radius retry,
+//                           dsm.cc:133-144) and all cells of tiles too dense for the shared-memory stage
 //
 // Membership (d2 < threshold) is evaluated with __dmul_rn/__dadd_rn (no FMA contraction) in the reference's
-// operation order, so neighbour sets and fallback levels are bit-exact decisions.  Heights differ from the CPU
-// only by the order of the double-precision summation.
+// operation order, so neighbour sets and retry levels are bit-exact decisions.  Heights differ from the CPU only
+// by the order of the double-precision summation and by z*(1/d2) replacing z/d2 (both O(1e-16) relative).
 #include <cfloat>
 #include <cmath>
 
@@ -52,6 +58,7 @@ constexpr int TJ = 32;              // tile extent along j
 constexpr int kGatherThreads = 256;
 constexpr int kStrip = 4;           // cells per thread in the gather kernel (adjacent along j)
 constexpr int kScanChunk = 4096;    // elements per block in the scan kernels (256 threads x 16)
+constexpr int kSortRegs = 4;        // bucket sort: records per lane held in registers (buckets up to 128 points)
 static_assert(TJ == kStrip * (kGatherThreads / 32), "one warp per strip row of the tile");
 
 struct PointRec {  // 32 bytes, one DRAM sector
@@ -61,17 +68,21 @@ struct PointRec {  // 32 bytes, one DRAM sector
 
 struct DsmPlan {
   int rows, cols_slab, col_begin;
-  int P;        // apron of the bin grid in cells (reach of the largest fallback threshold)
-  int W;        // window half-width of the primary threshold
-  int BR, BC;   // bin grid: (rows + 2P) x (cols_slab + 2P); bin (bi, bj) <-> cell (bi - P, col_begin + bj - P)
+  int W;          // window half-width (cells) of the primary threshold
+  int P;          // reach (cells) of the largest retry threshold
+  int Pa;         // apron of the bin grid (cells): P rounded up to a multiple of B
+  int B, Bshift;  // bucket edge in cells (power of two) and its log2
+  int BR, BC;     // fine bin grid (cells): bin (bi, bj) <-> cell (bi - Pa, gj0 + bj)
+  int KR, KC;     // bucket grid
+  int gj0;        // global column of bin column 0 (a multiple of TJ minus Pa: tiles align to GLOBAL columns)
+  int tile_j0;    // global tile index of the first tile column of this stripe
   double base_x, base_y;  // cell centre of index 0: pos + (0.5*length - 0.5*res)   (grid_map getPosition)
   double res, inv_res;
   double shift_x, shift_y;  // dsm.cc:42-43: x -= center_northing, y -= center_easting
   double thr0;
   int n_thr;
   double thr[kMaxThresholds];
-  short hw[kMaxHalfWidth + 1];   // half-width along i of the primary window at |dj|
-  short hwf[kMaxHalfWidth + 1];  // same for the largest fallback threshold
+  short hw[kMaxHalfWidth + 1];  // half-width along i of the primary window at |dj|
 };
 
 __device__ __forceinline__ double cell_x(const DsmPlan& p, int i) {
@@ -82,20 +93,41 @@ __device__ __forceinline__ double cell_y(const DsmPlan& p, int j_global) {
   return __dadd_rn(p.base_y, __dmul_rn(p.res, -static_cast<double>(j_global)));
 }
 
-// Bin of a shifted point, or -1 if it cannot reach any cell of this slab.  A point is assigned to the cell whose
-// centre is nearest; an off-by-one at a cell edge is harmless because membership is re-decided exactly by d2 and
-// every window carries half a cell of slack (see half_widths()).
-__device__ __forceinline__ long long bin_of(const DsmPlan& p, double px, double py) {
-  const double fi = floor((p.base_x - px) * p.inv_res + 0.5);
-  const double fj = floor((p.base_y - py) * p.inv_res + 0.5);
-  const double bi = fi + static_cast<double>(p.P);
-  const double bj = fj - static_cast<double>(p.col_begin) + static_cast<double>(p.P);
-  if (!(bi >= 0.0 && bi < static_cast<double>(p.BR) && bj >= 0.0 && bj < static_cast<double>(p.BC))) return -1;
-  return static_cast<long long>(bi) + static_cast<long long>(bj) * p.BR;
+// Fine bin (= nearest cell centre) of a shifted point; false if it lies outside the bin grid of this slab, i.e.
+// cannot reach any of its cells.  An off-by-one at a cell edge is harmless: membership is re-decided exactly by
+// d2 and every window carries half a cell of slack (see half_widths()).
+__device__ __forceinline__ bool fine_bin(const DsmPlan& p, double px, double py, int* bi, int* bj) {
+  const double fi = floor((p.base_x - px) * p.inv_res + 0.5) + static_cast<double>(p.Pa);
+  const double fj = floor((p.base_y - py) * p.inv_res + 0.5) - static_cast<double>(p.gj0);
+  if (!(fi >= 0.0 && fi < static_cast<double>(p.BR) && fj >= 0.0 && fj < static_cast<double>(p.BC))) return false;
+  *bi = static_cast<int>(fi);
+  *bj = static_cast<int>(fj);
+  return true;
+}
+
+// Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64) + one cubic correction
+// step.  Replaces the two IEEE divisions per neighbour of the reference (heights/d2 and 1/d2) by one reciprocal
+// and one FMA; the IDW height changes by O(1e-16) relative, far inside the float32 layer's rounding.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);  // |e| <= 2^-20
+  const double t = fma(e, e, e);     // e + e^2: r*(1 + e + e^2) leaves a relative error e^3 <= 2^-60
+  return fma(r, t, r);
+}
+
+// One 32-byte record = one 256-bit access (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256) = exactly one DRAM sector.
+__device__ __forceinline__ void store_rec(PointRec* dst, double x, double y, double z, unsigned long long idx) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(z),
+               "d"(__longlong_as_double(static_cast<long long>(idx)))
+               : "memory");
+}
+__device__ __forceinline__ void load_rec(const PointRec* src, double* x, double* y, double* z, double* idx_bits) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(*x), "=d"(*y), "=d"(*z), "=d"(*idx_bits) : "l"(src));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1: histogram
+// K1: bucket histogram.  count(b) goes to G[b + 2] so that after the inclusive scan G[b + 1] = start(b).
 __global__ void __launch_bounds__(256) dsm_count_kernel(const double* __restrict__ xyz, size_t n, DsmPlan plan,
                                                         unsigned int* __restrict__ G,
                                                         unsigned int* __restrict__ counters) {
@@ -104,8 +136,10 @@ __global__ void __launch_bounds__(256) dsm_count_kernel(const double* __restrict
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const double px = xyz[3 * t + 0] - plan.shift_x;
     const double py = xyz[3 * t + 1] - plan.shift_y;
-    const long long b = bin_of(plan, px, py);
-    if (b >= 0) {
+    int bi, bj;
+    if (fine_bin(plan, px, py, &bi, &bj)) {
+      const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
+                             static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
       atomicAdd(&G[b + 2], 1u);
       ++local;
     }
@@ -116,7 +150,7 @@ __global__ void __launch_bounds__(256) dsm_count_kernel(const double* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2: inclusive scan (reduce / spine / apply).  Plain HBM streaming: 3 reads + 1 write of the histogram.
+// K2: inclusive scan (reduce / spine / apply).
 __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total) {
   // `total` must point to shared memory; valid after return.
   __shared__ unsigned int warp_sums[32];
@@ -204,8 +238,8 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(uint4* __restrict__ dat
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: scatter.  H = G + 1 holds start(b) before this kernel; atomicAdd turns H[b] into start(b+1), i.e.
-// afterwards G[b] = start(b) for b in [0, nb].
+// K3: scatter.  G[b + 1] holds start(b) before this kernel; atomicAdd turns it into start(b + 1), i.e.
+// afterwards G[b] = start(b) for b in [0, nbuckets].
 __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restrict__ xyz, size_t n, DsmPlan plan,
                                                           unsigned int* __restrict__ G,
                                                           PointRec* __restrict__ rec) {
@@ -214,53 +248,79 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
     const double px = xyz[3 * t + 0] - plan.shift_x;
     const double py = xyz[3 * t + 1] - plan.shift_y;
     const double pz = xyz[3 * t + 2];
-    const long long b = bin_of(plan, px, py);
-    if (b >= 0) {
+    int bi, bj;
+    if (fine_bin(plan, px, py, &bi, &bj)) {
+      const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
+                             static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
       const unsigned int pos = atomicAdd(&G[b + 1], 1u);
-      double2* dst = reinterpret_cast<double2*>(rec + pos);
-      dst[0] = make_double2(px, py);
-      dst[1] = make_double2(pz, __longlong_as_double(static_cast<long long>(t)));
+      store_rec(rec + pos, px, py, pz, static_cast<unsigned long long>(t));
     }
   }
 }
 
-// K3b: canonical order inside every bin (ascending original index = what a stable sort would give).
-__global__ void __launch_bounds__(256) dsm_canon_kernel(const unsigned int* __restrict__ G, size_t nb,
-                                                        PointRec* __restrict__ rec) {
-  const size_t b = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (b >= nb) return;
-  const unsigned int s = G[b], e = G[b + 1];
-  if (e - s < 2) return;
-  for (unsigned int a = s + 1; a < e; ++a) {  // insertion sort; bins hold O(1) points for aerial densities
-    const PointRec key = rec[a];
-    unsigned int k = a;
-    while (k > s && rec[k - 1].idx > key.idx) {
-      rec[k] = rec[k - 1];
-      --k;
+// K3b: canonical order inside every bucket (ascending original index = what a stable sort would give), as an
+// index array: order[s + r] = position of the bucket's r-th smallest original index.  Only the warp-per-cell
+// kernel needs it (the tile kernel orders every cell's points in shared memory); writing 4 bytes per point
+// instead of permuting the 32-byte records keeps this pass at one read of the records.
+// One warp per bucket; every lane ranks its keys against all keys of the bucket (broadcast loads).
+__global__ void __launch_bounds__(256) dsm_bucket_order_kernel(const unsigned int* __restrict__ G,
+                                                               unsigned int n_buckets,
+                                                               const PointRec* __restrict__ rec,
+                                                               unsigned int* __restrict__ order) {
+  constexpr int kMaxK = 32 * kSortRegs;  // bucket sizes handled through shared memory
+  __shared__ __align__(16) unsigned int skeys[8][kMaxK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (unsigned int b = blockIdx.x * (blockDim.x >> 5) + warp; b < n_buckets; b += warps_total) {
+    const unsigned int s = G[b], e = G[b + 1];
+    const unsigned int k = e - s;
+    if (k == 0) continue;
+    if (k <= static_cast<unsigned int>(kMaxK)) {
+      // original indices are < 2^32 (n is checked on the host): compare their low words
+      unsigned int key[kSortRegs], rank[kSortRegs];
+#pragma unroll
+      for (int r = 0; r < kSortRegs; ++r) {
+        const unsigned int q = lane + 32u * r;
+        key[r] = q < k ? static_cast<unsigned int>(__ldg(&rec[s + q].idx)) : 0xffffffffu;
+        rank[r] = 0;
+        skeys[warp][q] = key[r];  // slots >= k hold 0xffffffff: never smaller than a real key
+      }
+      __syncwarp();
+      const unsigned int k4 = (k + 3u) >> 2;
+      const uint4* sk4 = reinterpret_cast<const uint4*>(skeys[warp]);
+      for (unsigned int q = 0; q < k4; ++q) {
+        const uint4 o = sk4[q];  // broadcast
+#pragma unroll
+        for (int r = 0; r < kSortRegs; ++r)
+          rank[r] += (o.x < key[r] ? 1u : 0u) + (o.y < key[r] ? 1u : 0u) + (o.z < key[r] ? 1u : 0u) +
+                     (o.w < key[r] ? 1u : 0u);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < kSortRegs; ++r) {
+        const unsigned int q = lane + 32u * r;
+        if (q < k) order[s + rank[r]] = s + q;
+      }
+    } else {
+      // far denser than the bucket size was chosen for: rank against the keys in global memory
+      for (unsigned int q = lane; q < k; q += 32) {
+        const unsigned long long mine = __ldg(&rec[s + q].idx);
+        unsigned int rank = 0;
+        for (unsigned int o = 0; o < k; ++o) rank += __ldg(&rec[s + o].idx) < mine ? 1u : 0u;
+        order[s + rank] = s + q;
+      }
     }
-    if (k != a) rec[k] = key;
   }
-}
-
-// Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~2^-23) + one cubic
-// correction step.  Replaces the two IEEE divisions per neighbour of the reference (heights/d2 and 1/d2) by one reciprocal
-// and one FMA; the IDW height changes by O(1e-16) relative, far inside the float32 layer's rounding.
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  const double e = fma(-x, r, 1.0);  // |e| <= 2^-23
-  const double t = fma(e, e, e);     // e + e^2: r*(1 + e + e^2) leaves a relative error e^3 <= 2^-69
-  return fma(r, t, r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // K4: tile gather
 struct GatherArgs {
-  const unsigned int* G;
+  const unsigned int* G;   // bucket starts
   const PointRec* rec;
   float* elevation;
-  unsigned int* empty_list;
-  unsigned int* counters;  // [0] empty count, [1] error flag
+  unsigned int* cell_list;  // cells handed to the warp-per-cell kernel
+  unsigned int* counters;   // [0] list length, [1] coincident-point flag, [3] dense tiles
   int* dbg_count;
   signed char* dbg_level;
   int capacity;  // points that fit the shared-memory stage
@@ -270,19 +330,21 @@ struct GatherArgs {
 // Per-thread work of the gather kernel.  A thread owns kStrip cells with the same i and adjacent j; their windows
 // overlap in all but one bin row, so every staged point is loaded once, (qx - px)^2 is computed once, and only
 // the (qy - py)^2 + compare + accumulate part is per cell.  The thread walks the kStrip + 2W bin rows of its
-// strip as ONE flattened loop (lanes stay busy until their own candidates run out); per row, `srow` gives the
-// half-width of the widest window among the strip's cells and the mask of cells that row can reach.
-// Accumulation order per cell: bin rows ascending, points ascending inside a row == canonical bin order.
-template <bool STAGED, bool DEBUG>
-__device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherArgs& args, int off_srow, int off_sxy,
-                                             int off_spz, int i0, int j0) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];  // addressed by byte offset: plain LDS, no generic ptr
+// strip as ONE flattened loop (lanes stay busy until their own candidates run out); `srow[r]` is the half-width
+// of the widest window among the strip's cells on row r.
+// Accumulation order per cell: bin rows ascending, points ascending inside a row == canonical order.
+// Shared memory is addressed by byte offset (plain LDS, no generic pointers):
+//   off_A    uint32 A[NJw*NIw + 2]: A[lin] = start of bin lin, A[lin + 1] = its end (bins are i-fastest)
+template <bool DEBUG>
+__device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherArgs& args, int off_A, int off_srow,
+                                             int off_sxy, int off_spz, int i0, int jl0_tile) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = plan.W;
-  const int NI = TI + 2 * W + 1;
+  const int NIw = TI + 2 * W;
   const int ti = threadIdx.x & 31;
   const int tq = threadIdx.x >> 5;  // warp index == strip index along j (warp-uniform)
   const int i = i0 + ti;
-  const int jl0 = j0 + kStrip * tq;
+  const int jl0 = jl0_tile + kStrip * tq;  // slab-local column of the strip's first cell (< 0 left of the stripe)
   const double qx = cell_x(plan, i);
   const double thr0 = plan.thr0;
   double qy[kStrip], num[kStrip], den[kStrip];
@@ -294,11 +356,11 @@ __device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherAr
     num[m] = 0.0;
     den[m] = 0.0;
     cnt[m] = 0;
-    if (i < plan.rows && jl0 + m < plan.cols_slab) cellmask |= 1u << m;
+    if (i < plan.rows && jl0 + m >= 0 && jl0 + m < plan.cols_slab) cellmask |= 1u << m;
   }
   const int n_rows = kStrip + 2 * W;
-  int r = -1;                                                    // row of the strip's window
-  int row_addr = ((kStrip * tq - 1) * NI + ti + W) * 4;          // byte offset of soff[row][ti + W]
+  int r = -1;                                                      // row of the strip's window
+  int lin_addr = off_A + ((kStrip * tq - 1) * NIw + ti + W) * 4;   // byte offset of A[lin], lin = bin (i, row r)
   unsigned int k = 0, e = 0;
   if (cellmask) {
     for (;;) {
@@ -306,12 +368,12 @@ __device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherAr
         bool found = false;
         while (r + 1 < n_rows) {
           ++r;
-          row_addr += NI * 4;
-          const int info = *reinterpret_cast<const int*>(smem_raw + off_srow + 4 * r);  // (h << 8) | mask, or -1
-          if (info < 0) continue;
-          const int h4 = (info >> 8) * 4;
-          k = *reinterpret_cast<const unsigned int*>(smem_raw + row_addr - h4);
-          e = *reinterpret_cast<const unsigned int*>(smem_raw + row_addr + h4 + 4);
+          lin_addr += NIw * 4;
+          const int h = *reinterpret_cast<const int*>(smem_raw + off_srow + 4 * r);
+          if (h < 0) continue;
+          // bins [i - h, i + h] of this row: points [A[lin - h], A[lin + h + 1])
+          k = *reinterpret_cast<const unsigned int*>(smem_raw + lin_addr - 4 * h);
+          e = *reinterpret_cast<const unsigned int*>(smem_raw + lin_addr + 4 * h + 4);
           if (k < e) {
             found = true;
             break;
@@ -319,15 +381,8 @@ __device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherAr
         }
         if (!found) break;
       }
-      double2 p;
-      double pz;
-      if (STAGED) {
-        p = *reinterpret_cast<const double2*>(smem_raw + off_sxy + 16 * k);
-        pz = *reinterpret_cast<const double*>(smem_raw + off_spz + 8 * k);
-      } else {
-        p = __ldg(reinterpret_cast<const double2*>(args.rec + k));
-        pz = __ldg(reinterpret_cast<const double*>(args.rec + k) + 2);
-      }
+      const double2 p = *reinterpret_cast<const double2*>(smem_raw + off_sxy + 16 * k);
+      const double pz = *reinterpret_cast<const double*>(smem_raw + off_spz + 8 * k);
       const double dx = qx - p.x;
       const double dx2 = __dmul_rn(dx, dx);
       // Branch-free: every cell of the strip tests every staged point of the strip's rows.  A bin row that is out
@@ -373,7 +428,7 @@ __device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherAr
       unsigned int base = 0;
       if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (is_empty) args.empty_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
+      if (is_empty) args.cell_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
     }
   }
   if (coincident) atomicExch(&args.counters[1], 1u);
@@ -382,154 +437,221 @@ __device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherAr
 __global__ void __launch_bounds__(kGatherThreads)
     dsm_gather_kernel(const __grid_constant__ DsmPlan plan, const GatherArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned int s_total;
+  __shared__ unsigned int s_runs;
+  __shared__ unsigned int s_scan_total;
   const int W = plan.W;
-  const int NC = TJ + 2 * W;      // staged bin columns
-  const int NI = TI + 2 * W + 1;  // offsets per column (one past the last bin)
-  unsigned int* soff = reinterpret_cast<unsigned int*>(smem_raw);           // [NC][NI]
-  unsigned int* colbase = soff + NC * NI;                                    // [NC + 1] local start of a column
-  unsigned int* colg0 = colbase + (NC + 1);                                  // [NC] global start of a column
-  int* srow = reinterpret_cast<int*>(colg0 + NC);                            // [kStrip + 2W] strip row table
-  size_t off_bytes = (static_cast<size_t>(NC) * NI + 2 * NC + 1 + kStrip + 2 * W) * sizeof(unsigned int);
+  const int NIw = TI + 2 * W, NJw = TJ + 2 * W;  // window of the tile in fine bins
+  const int N = NIw * NJw;
+  const int n_strip_rows = kStrip + 2 * W;
+  // carve: A[N + 2] | srow[kStrip + 2W] | run_pre[max_runs + 1] | run_g0[max_runs] | xy | z | idx
+  unsigned int* A = reinterpret_cast<unsigned int*>(smem_raw);
+  int* srow = reinterpret_cast<int*>(A + N + 2);
+  const int max_runs = (NJw + plan.B - 1) / plan.B + 1;  // bucket rows overlapping the window
+  unsigned int* run_pre = reinterpret_cast<unsigned int*>(srow + n_strip_rows);
+  unsigned int* run_g0 = run_pre + max_runs + 1;
+  size_t off_bytes = (static_cast<size_t>(N) + 2 + n_strip_rows + 2 * max_runs + 1) * 4;
   off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
-  double2* sxy = reinterpret_cast<double2*>(smem_raw + off_bytes);  // (x, y) of the staged points
-  double* spz = reinterpret_cast<double*>(sxy + args.capacity);
+  const int off_sxy = static_cast<int>(off_bytes);
+  const int off_spz = off_sxy + 16 * args.capacity;
+  const int off_sidx = off_spz + 8 * args.capacity;
+  double2* sxy = reinterpret_cast<double2*>(smem_raw + off_sxy);
+  double* spz = reinterpret_cast<double*>(smem_raw + off_spz);
+  unsigned int* sidx = reinterpret_cast<unsigned int*>(smem_raw + off_sidx);
 
   const int tile_i = blockIdx.x % args.tiles_i;
   const int tile_j = blockIdx.x / args.tiles_i;
   const int i0 = tile_i * TI;
-  const int j0 = tile_j * TJ;  // local column in the slab
+  const int gj_tile = (plan.tile_j0 + tile_j) * TJ;  // global column of the tile's first cell
+  const int jl0_tile = gj_tile - plan.col_begin;      // slab-local (negative if the tile starts left of the stripe)
+  const int wi0 = i0 + plan.Pa - W;                   // window origin in fine bins (>= 0: Pa >= W)
+  const int wj0 = gj_tile - plan.gj0 - W;
 
-  for (int r = threadIdx.x; r < kStrip + 2 * W; r += kGatherThreads) {
+  // 0. tables: strip rows, zeroed cell counters, bucket runs (one contiguous record range per bucket row)
+  for (int r = threadIdx.x; r < n_strip_rows; r += kGatherThreads) {
     // strip row r is bin row (first cell's j) - W + r; cell m of the strip sees it at dj = r - W - m
-    int hmax = -1, mask = 0;
+    int hmax = -1;
     for (int m = 0; m < kStrip; ++m) {
       const int dj = r - W - m;
       const int ad = dj < 0 ? -dj : dj;
       const int h = ad <= W ? plan.hw[ad] : -1;
-      if (h >= 0) {
-        mask |= 1 << m;
-        hmax = max(hmax, h);
-      }
+      hmax = max(hmax, h);
     }
-    srow[r] = hmax < 0 ? -1 : ((hmax << 8) | mask);
+    srow[r] = hmax;
   }
-  // 1. bin start offsets of the tile + apron (global values)
-  for (int e = threadIdx.x; e < NC * NI; e += kGatherThreads) {
-    const int jj = e / NI, ii = e - jj * NI;
-    const int bj = j0 - W + jj + plan.P;  // >= 0 because P >= W
-    int bi = i0 - W + ii + plan.P;
-    unsigned int v;
-    if (bj >= plan.BC) {
-      v = 0xffffffffu;  // marks "no such column": handled below as an empty column
-    } else {
-      bi = min(bi, plan.BR);  // bin BR of a row is the first bin of the next row: its start ends this row
-      v = args.G[static_cast<size_t>(bj) * plan.BR + bi];
+  for (int e = threadIdx.x; e < N + 2; e += kGatherThreads) A[e] = 0;
+  const int kbi0 = wi0 >> plan.Bshift;
+  const int kbi1 = min(wi0 + NIw - 1, plan.BR - 1) >> plan.Bshift;
+  const int kbj0 = wj0 >> plan.Bshift;
+  const int kbj1 = min(wj0 + NJw - 1, plan.BC - 1) >> plan.Bshift;
+  const int n_runs = kbj1 - kbj0 + 1;
+  if (threadIdx.x == 0) {
+    unsigned int acc = 0;
+    for (int q = 0; q < n_runs; ++q) {
+      const size_t row = static_cast<size_t>(kbj0 + q) * plan.KR;
+      const unsigned int g0 = args.G[row + kbi0];
+      const unsigned int g1 = args.G[row + kbi1 + 1];
+      run_pre[q] = acc;
+      run_g0[q] = g0;
+      acc += g1 - g0;
     }
-    soff[e] = v;
-  }
-  __syncthreads();
-  // 2. column lengths -> local bases
-  if (threadIdx.x < 32) {
-    unsigned int carry = 0;
-    for (int base = 0; base < NC; base += 32) {
-      const int jj = base + threadIdx.x;
-      unsigned int len = 0, g0 = 0;
-      if (jj < NC) {
-        g0 = soff[jj * NI];
-        const unsigned int g1 = soff[jj * NI + NI - 1];
-        len = (g0 == 0xffffffffu) ? 0u : (g1 - g0);
-        if (g0 == 0xffffffffu) g0 = 0;
-      }
-      unsigned int inc = len;
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((threadIdx.x & 31) >= o) inc += t;
-      }
-      if (jj < NC) {
-        colbase[jj] = carry + inc - len;
-        colg0[jj] = g0;
-      }
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (threadIdx.x == 0) colbase[NC] = carry;
+    run_pre[n_runs] = acc;
+    s_runs = acc;
+    s_total = 0;
   }
   __syncthreads();
-  const unsigned int tile_points = colbase[NC];
-  const bool staged = tile_points <= static_cast<unsigned int>(args.capacity);
-  // 3. stage the records (SoA doubles) and rebase the offsets
-  if (staged) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int jj = warp; jj < NC; jj += kGatherThreads / 32) {
-      const unsigned int len = colbase[jj + 1] - colbase[jj];
-      const PointRec* src = args.rec + colg0[jj];
-      const unsigned int dst = colbase[jj];
-      for (unsigned int k = lane; k < len; k += 32) {
-        sxy[dst + k] = __ldg(reinterpret_cast<const double2*>(src + k));
-        spz[dst + k] = __ldg(reinterpret_cast<const double*>(src + k) + 2);
+  const unsigned int n_in = s_runs;  // points of the buckets overlapping the window
+
+  // 1. count the window's points per cell (shared-memory atomics): bin lin is counted in A[2 + lin], so that the
+  //    inclusive scan below leaves A[1 + lin] = start(lin).
+  bool dense = n_in > 4u * static_cast<unsigned int>(args.capacity);  // cannot fit whatever the window keeps
+  if (!dense) {
+    unsigned int kept = 0;
+    for (unsigned int q = threadIdx.x; q < n_in; q += kGatherThreads) {
+      int run = 0;
+      while (q >= run_pre[run + 1]) ++run;
+      const PointRec* pr = args.rec + run_g0[run] + (q - run_pre[run]);
+      const double2 xy = __ldg(reinterpret_cast<const double2*>(pr));
+      int bi, bj;
+      if (fine_bin(plan, xy.x, xy.y, &bi, &bj)) {
+        const int ii = bi - wi0, jj = bj - wj0;
+        if (ii >= 0 && ii < NIw && jj >= 0 && jj < NJw) {
+          atomicAdd(&A[2 + jj * NIw + ii], 1u);
+          ++kept;
+        }
       }
     }
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xffffffffu, kept, o);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&s_total, kept);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < NC * NI; e += kGatherThreads) {
-    const int jj = e / NI;
-    const unsigned int v = soff[e];
-    if (v == 0xffffffffu) {
-      soff[e] = 0;  // empty column: every range [0,0)
-    } else if (staged) {
-      soff[e] = v - colg0[jj] + colbase[jj];
+  dense = dense || s_total > static_cast<unsigned int>(args.capacity);
+  if (dense) {
+    // Too many points for the stage (density far above the average it was sized for): every cell of the tile is
+    // evaluated by the warp-per-cell kernel instead.  The decision depends only on the tile's points, and tiles
+    // are aligned to global columns, so it is the same for every striping of the map.
+    if (threadIdx.x == 0) atomicAdd(&args.counters[3], 1u);
+    const int ti = threadIdx.x & 31, tq = threadIdx.x >> 5;
+    for (int m = 0; m < kStrip; ++m) {
+      const int i = i0 + ti, jl = jl0_tile + kStrip * tq + m;
+      const bool valid = i < plan.rows && jl >= 0 && jl < plan.cols_slab;
+      const unsigned int mask = __ballot_sync(0xffffffffu, valid);
+      if (mask) {
+        const int leader = __ffs(mask) - 1;
+        unsigned int base = 0;
+        if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid)
+          args.cell_list[base + __popc(mask & ((1u << ti) - 1u))] =
+              static_cast<unsigned int>(static_cast<size_t>(jl) * plan.rows + i);
+      }
+    }
+    return;
+  }
+
+  // 2. inclusive scan of A[0 .. N + 1] in place: thread t owns a contiguous chunk
+  {
+    const int per = (N + 2 + kGatherThreads - 1) / kGatherThreads;
+    const int lo = min(static_cast<int>(threadIdx.x) * per, N + 2), hi = min(lo + per, N + 2);
+    unsigned int s = 0;
+    for (int e = lo; e < hi; ++e) s += A[e];
+    unsigned int run = block_exclusive_scan(s, &s_scan_total);
+    for (int e = lo; e < hi; ++e) {
+      run += A[e];
+      A[e] = run;
     }
   }
   __syncthreads();
 
-  // 4. per-cell gather: every thread owns a 1 x kStrip strip of cells (same i, adjacent j)
-  const int off_srow = static_cast<int>(reinterpret_cast<unsigned char*>(srow) - smem_raw);
-  const int off_sxy = static_cast<int>(off_bytes);
-  const int off_spz = off_sxy + 16 * args.capacity;
-  if (args.dbg_count) {  // tests: also record result_set.size() per cell
-    if (staged) {
-      gather_strip<true, true>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
-    } else {
-      gather_strip<false, true>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
+  // 3. scatter the window's points into cell order: A[1 + lin] is the cursor of bin lin; afterwards
+  //    A[1 + lin] = start(lin + 1), i.e. A[lin] = start(lin) (A[0] = 0) — the layout gather_strip reads.
+  for (unsigned int q = threadIdx.x; q < n_in; q += kGatherThreads) {
+    int run = 0;
+    while (q >= run_pre[run + 1]) ++run;
+    const PointRec* pr = args.rec + run_g0[run] + (q - run_pre[run]);
+    double x, y, z, ib;
+    load_rec(pr, &x, &y, &z, &ib);
+    int bi, bj;
+    if (fine_bin(plan, x, y, &bi, &bj)) {
+      const int ii = bi - wi0, jj = bj - wj0;
+      if (ii >= 0 && ii < NIw && jj >= 0 && jj < NJw) {
+        const unsigned int pos = atomicAdd(&A[1 + jj * NIw + ii], 1u);
+        sxy[pos] = make_double2(x, y);
+        spz[pos] = z;
+        sidx[pos] = static_cast<unsigned int>(__double_as_longlong(ib));
+      }
     }
-  } else if (staged) {
-    gather_strip<true, false>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
+  }
+  __syncthreads();
+
+  // 4. canonical order inside every cell: ascending original index
+  for (int lin = threadIdx.x; lin < N; lin += kGatherThreads) {
+    const unsigned int s = A[lin], e = A[lin + 1];
+    for (unsigned int a = s + 1; a < e; ++a) {
+      const unsigned int key = sidx[a];
+      if (sidx[a - 1] <= key) continue;
+      const double2 kxy = sxy[a];
+      const double kz = spz[a];
+      unsigned int q = a;
+      while (q > s && sidx[q - 1] > key) {
+        sidx[q] = sidx[q - 1];
+        sxy[q] = sxy[q - 1];
+        spz[q] = spz[q - 1];
+        --q;
+      }
+      sidx[q] = key;
+      sxy[q] = kxy;
+      spz[q] = kz;
+    }
+  }
+  __syncthreads();
+
+  // 5. per-cell gather: every thread owns a 1 x kStrip strip of cells (same i, adjacent j)
+  const int off_srow = static_cast<int>(reinterpret_cast<unsigned char*>(srow) - smem_raw);
+  if (args.dbg_count) {  // tests: also record result_set.size() per cell
+    gather_strip<true>(plan, args, 0, off_srow, off_sxy, off_spz, i0, jl0_tile);
   } else {
-    gather_strip<false, false>(plan, args, off_srow, off_sxy, off_spz, i0, j0);
+    gather_strip<false>(plan, args, 0, off_srow, off_sxy, off_spz, i0, jl0_tile);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K5: expanding-radius retry for the cells the primary threshold left empty (dsm.cc:133-144).
-struct FillArgs {
+// K5: one warp per listed cell.  Evaluates the reference's complete per-cell sequence (primary query, then the
+// expanding-radius retry dsm.cc:133-144) from the bucket records in HBM: cells left empty by the tile kernel and
+// every cell of a tile too dense for the shared-memory stage.
+struct CellArgs {
   const unsigned int* G;
+  const unsigned int* order;  // canonical visiting order of the bucket records
   const PointRec* rec;
   float* elevation;
-  const unsigned int* empty_list;
+  const unsigned int* cell_list;
   unsigned int* counters;
   int* dbg_count;
   signed char* dbg_level;
 };
 
-__global__ void __launch_bounds__(256) dsm_fill_kernel(const __grid_constant__ DsmPlan plan, const FillArgs args) {
+__global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ DsmPlan plan, const CellArgs args) {
   const int lane = threadIdx.x & 31;
-  const unsigned int n_empty = args.counters[0];
+  const unsigned int n_cells = args.counters[0];
   const unsigned int warps_total = gridDim.x * (blockDim.x >> 5);
   const int P = plan.P;
-  for (unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n_empty; c += warps_total) {
-    const unsigned int cell = args.empty_list[c];
+  for (unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n_cells; c += warps_total) {
+    const unsigned int cell = args.cell_list[c];
     const int i = static_cast<int>(cell % static_cast<unsigned int>(plan.rows));
     const int jl = static_cast<int>(cell / static_cast<unsigned int>(plan.rows));
     const double qx = cell_x(plan, i);
     const double qy = cell_y(plan, plan.col_begin + jl);
-    // pass 1: smallest d2 in the window of the largest threshold
+    // buckets overlapping the window of the largest threshold (fine bins [b - P, b + P] on both axes)
+    const int bi = i + plan.Pa, bj = plan.col_begin + jl - plan.gj0;
+    const int kbi0 = max(bi - P, 0) >> plan.Bshift, kbi1 = min(bi + P, plan.BR - 1) >> plan.Bshift;
+    const int kbj0 = max(bj - P, 0) >> plan.Bshift, kbj1 = min(bj + P, plan.BC - 1) >> plan.Bshift;
+    // pass 1: smallest d2
     double dmin = DBL_MAX;
-    for (int dj = -P; dj <= P; ++dj) {
-      const int h = plan.hwf[dj < 0 ? -dj : dj];
-      if (h < 0) continue;
-      const size_t row = static_cast<size_t>(jl + P + dj) * plan.BR;
-      const unsigned int a = args.G[row + (i + P - h)];
-      const unsigned int b = args.G[row + (i + P + h + 1)];
-      for (unsigned int k = a + lane; k < b; k += 32) {
+    for (int kj = kbj0; kj <= kbj1; ++kj) {
+      const size_t row = static_cast<size_t>(kj) * plan.KR;
+      const unsigned int a = args.G[row + kbi0];
+      const unsigned int b = args.G[row + kbi1 + 1];
+      for (unsigned int k = a + lane; k < b; k += 32) {  // min is order-independent: no indirection needed
         const double2 v = __ldg(reinterpret_cast<const double2*>(args.rec + k));
         const double dx = qx - v.x;
         const double dy = qy - v.y;
@@ -537,7 +659,7 @@ __global__ void __launch_bounds__(256) dsm_fill_kernel(const __grid_constant__ D
       }
     }
     for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    // first retry threshold whose (strict) ball is non-empty
+    // first threshold whose (strict) ball is non-empty: k = 0 is the primary query itself
     int level = -1;
     for (int k = 0; k < plan.n_thr; ++k) {
       if (dmin < plan.thr[k]) {
@@ -545,24 +667,29 @@ __global__ void __launch_bounds__(256) dsm_fill_kernel(const __grid_constant__ D
         break;
       }
     }
-    if (level < 0) continue;  // stays untouched (NaN or the previous elevation)
+    if (level < 0) {  // stays untouched (NaN or the previous elevation)
+      if (args.dbg_count && lane == 0) {
+        args.dbg_count[cell] = 0;
+        args.dbg_level[cell] = -1;
+      }
+      continue;
+    }
     const double thr = plan.thr[level];
     double num = 0.0, den = 0.0;
     int cnt = 0;
     bool coincident = false;
-    for (int dj = -P; dj <= P; ++dj) {
-      const int h = plan.hwf[dj < 0 ? -dj : dj];
-      if (h < 0) continue;
-      const size_t row = static_cast<size_t>(jl + P + dj) * plan.BR;
-      const unsigned int a = args.G[row + (i + P - h)];
-      const unsigned int b = args.G[row + (i + P + h + 1)];
+    for (int kj = kbj0; kj <= kbj1; ++kj) {
+      const size_t row = static_cast<size_t>(kj) * plan.KR;
+      const unsigned int a = args.G[row + kbi0];
+      const unsigned int b = args.G[row + kbi1 + 1];
       for (unsigned int k = a + lane; k < b; k += 32) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(args.rec + k));
+        const PointRec* pr = args.rec + __ldg(args.order + k);  // canonical order: lane partial sums are fixed
+        const double2 v = __ldg(reinterpret_cast<const double2*>(pr));
         const double dx = qx - v.x;
         const double dy = qy - v.y;
         const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         if (d2 < thr) {
-          const double pz = __ldg(reinterpret_cast<const double*>(args.rec + k) + 2);
+          const double pz = __ldg(reinterpret_cast<const double*>(pr) + 2);
           ++cnt;
           const double w = fast_rcp(d2);
           num = fma(pz, w, num);
@@ -611,6 +738,8 @@ void half_widths(double thr, double res, int W, short* out) {
   }
 }
 
+inline int round_up(int v, int m) { return ((v + m - 1) / m) * m; }
+
 }  // namespace
 
 int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius, double center_easting,
@@ -646,13 +775,31 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_r
   plan.P = static_cast<int>(std::floor(std::sqrt(thr_max) / g.resolution + 0.5 + slack));
   plan.P = std::max(plan.P, plan.W);
   if (plan.P > kMaxHalfWidth) return AMB_ERR_UNSUPPORTED;  // resolution far finer than the search radius
-  plan.BR = plan.rows + 2 * plan.P;
-  plan.BC = plan.cols_slab + 2 * plan.P;
   half_widths(plan.thr0, g.resolution, plan.W, plan.hw);
-  half_widths(thr_max, g.resolution, plan.P, plan.hwf);
 
-  const size_t nb = static_cast<size_t>(plan.BR) * plan.BC;
-  const size_t g_elems = ((nb + 2 + 3) / 4) * 4;  // uint4-aligned length
+  // Bucket edge: a power of two (<= 16 cells) such that a bucket holds a few dozen points at the cloud's average
+  // density over the map (the points actually binned may be fewer: that only makes buckets emptier).
+  const double per_cell = static_cast<double>(n) / (static_cast<double>(g.rows) * static_cast<double>(g.cols));
+  int B = 1, shift = 0;
+  while (B < 16 && per_cell * (2.0 * B) * (2.0 * B) <= 48.0) {
+    B *= 2;
+    ++shift;
+  }
+  plan.B = B;
+  plan.Bshift = shift;
+  plan.Pa = round_up(plan.P, B);
+  // Tiles align to GLOBAL columns (multiples of TJ), so that the content of a tile — hence the shared-memory /
+  // warp-per-cell path decision and every summation order — does not depend on how the map is striped.
+  plan.tile_j0 = ctx->col_begin / TJ;
+  const int tile_j1 = (ctx->col_end - 1) / TJ;  // last tile column (inclusive)
+  plan.gj0 = plan.tile_j0 * TJ - plan.Pa;
+  plan.BR = round_up(round_up(g.rows, TI) + 2 * plan.Pa, B);
+  plan.BC = round_up((tile_j1 + 1) * TJ + plan.Pa - plan.gj0, B);
+  plan.KR = plan.BR / B;
+  plan.KC = plan.BC / B;
+
+  const size_t nbk = static_cast<size_t>(plan.KR) * plan.KC;
+  const size_t g_elems = ((nbk + 2 + 3) / 4) * 4;  // uint4-aligned length
   const size_t n_vec = g_elems / 4;
   const int scan_blocks = static_cast<int>((n_vec + kScanChunk / 4 - 1) / (kScanChunk / 4));
   const size_t cells = ctx->slab_cells();
@@ -660,6 +807,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_r
   AMB_CUDA(ctx, ctx->bin_starts.reserve(g_elems * sizeof(unsigned int)));
   AMB_CUDA(ctx, ctx->block_sums.reserve(static_cast<size_t>(scan_blocks) * sizeof(unsigned int)));
   AMB_CUDA(ctx, ctx->records.reserve(n * sizeof(PointRec)));
+  AMB_CUDA(ctx, ctx->point_order.reserve(n * sizeof(unsigned int)));
   AMB_CUDA(ctx, ctx->empty_cells.reserve(cells * sizeof(unsigned int)));
   AMB_CUDA(ctx, ctx->counters.reserve(64));
   if (ctx->dsm_debug) {
@@ -687,52 +835,55 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_r
   scan_apply_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(G), n_vec,
                                                 ctx->block_sums.as<unsigned int>());
   dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n, plan, G, rec);
-  dsm_canon_kernel<<<static_cast<unsigned int>((nb + 255) / 256), 256, 0, s>>>(G, nb, rec);
+  dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
+                                                      ctx->point_order.as<unsigned int>());
   ctx->dsm_launches += 6;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BIN_END], s));
 
   // gather
   const int W = plan.W;
-  const int NC = TJ + 2 * W, NI = TI + 2 * W + 1;
-  size_t off_bytes = (static_cast<size_t>(NC) * NI + 2 * NC + 1 + kStrip + 2 * W) * sizeof(unsigned int);
+  const int NIw = TI + 2 * W, NJw = TJ + 2 * W;
+  const int max_runs = (NJw + B - 1) / B + 1;
+  size_t off_bytes = (static_cast<size_t>(NIw) * NJw + 2 + kStrip + 2 * W + 2 * max_runs + 1) * 4;
   off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
-  // Stage size: 1.6x the expected number of points in a tile + apron under a uniform density (the tail of a
-  // Poisson count is far inside that; denser tiles fall back to global reads), clamped to [24 KB, 100 KB] so that
-  // several blocks stay resident per SM (227 KB usable).
-  if (off_bytes + 3 * sizeof(double) * 64 > 200 * 1024) return AMB_ERR_UNSUPPORTED;
-  const double avg_per_bin = static_cast<double>(n) / static_cast<double>(nb);
-  const double expect = avg_per_bin * static_cast<double>(NC) * static_cast<double>(NI - 1);
-  size_t smem = off_bytes + static_cast<size_t>(1.6 * expect + 64.0) * 3 * sizeof(double);
+  const size_t per_point = 16 + 8 + 4;
+  // Stage size: 1.6x the expected number of points in a tile window under a uniform density (the tail of a
+  // Poisson count is far inside that; denser tiles go to the warp-per-cell kernel), clamped to [24 KB, 100 KB]
+  // so that several blocks stay resident per SM (227 KB usable).
+  if (off_bytes + per_point * 64 > 200 * 1024) return AMB_ERR_UNSUPPORTED;
+  const double expect = per_cell * static_cast<double>(NIw) * static_cast<double>(NJw);
+  size_t smem = off_bytes + static_cast<size_t>(1.6 * expect + 64.0) * per_point;
   smem = std::min<size_t>(std::max<size_t>(smem, 24 * 1024), 100 * 1024);
-  smem = std::max(smem, off_bytes + 3 * sizeof(double) * 64);
+  smem = std::max(smem, off_bytes + per_point * 64);
   smem = (smem + 1023) & ~static_cast<size_t>(1023);
-  int capacity = static_cast<int>((smem - off_bytes) / (3 * sizeof(double)));
+  const int capacity = static_cast<int>((smem - off_bytes) / per_point) & ~1;
   GatherArgs ga;
   ga.G = G;
   ga.rec = rec;
   ga.elevation = ctx->layers[AMB_LAYER_ELEVATION];
-  ga.empty_list = ctx->empty_cells.as<unsigned int>();
+  ga.cell_list = ctx->empty_cells.as<unsigned int>();
   ga.counters = counters;
   ga.dbg_count = ctx->dsm_debug ? ctx->dbg_count.as<int>() : nullptr;
   ga.dbg_level = ctx->dsm_debug ? ctx->dbg_level.as<signed char>() : nullptr;
   ga.capacity = capacity;
   ga.tiles_i = (plan.rows + TI - 1) / TI;
-  const int tiles_j = (plan.cols_slab + TJ - 1) / TJ;
+  const int tiles_j = tile_j1 - plan.tile_j0 + 1;
   AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
   dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
   ctx->dsm_launches += 1;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));
 
-  FillArgs fa;
-  fa.G = G;
-  fa.rec = rec;
-  fa.elevation = ga.elevation;
-  fa.empty_list = ga.empty_list;
-  fa.counters = counters;
-  fa.dbg_count = ga.dbg_count;
-  fa.dbg_level = ga.dbg_level;
-  dsm_fill_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(plan, fa);
+  CellArgs ca;
+  ca.G = G;
+  ca.order = ctx->point_order.as<unsigned int>();
+  ca.rec = rec;
+  ca.elevation = ga.elevation;
+  ca.cell_list = ga.cell_list;
+  ca.counters = counters;
+  ca.dbg_count = ga.dbg_count;
+  ca.dbg_level = ga.dbg_level;
+  dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(plan, ca);
   ctx->dsm_launches += 1;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
   AMB_CUDA(ctx, cudaGetLastError());

@@ -40,7 +40,7 @@ struct OrthoArgs {
   float* observation_index;
   float* out_layer;               // `ortho` (gray) or `colored_ortho` (packed colour bits)
   const uint8_t* const* images;   // device array: frame -> device raster
-  const double* cull_data;        // device array [n_frames][6]: camera centre, optical axis (map frame)
+  const double* cull_data;        // device array [n_frames][12]: camera centre, R_C_G rows (map frame)
   unsigned int* error_flag;
   size_t row_step;
   int n_frames, frame_base;       // frames in this launch; index of its first frame within the process() call
@@ -49,17 +49,29 @@ struct OrthoArgs {
   int dist_type;
   int do_cull;                    // 0: brute force over all frames
   int cone;                       // 1: view-cone test active (else only "behind the camera")
+  int rect;                       // 1: view-rectangle test active (bounds on the undistorted normalised keypoint)
+  double u_lo, u_hi, v_lo, v_hi;  // visible  =>  u in [u_lo, u_hi], v in [v_lo, v_hi]   (u = x_c/z_c, v = y_c/z_c)
+  double nu_lo, nu_hi, nv_lo, nv_hi;  // sqrt(1 + bound^2): norms of the bounding planes' normals
   double base_x, base_y, res;
   double fu, fv, cu, cv;
   double d0, d1, d2, d3;
   double cos_c, sin_c;            // half-angle of the conservative view cone
 };
 
+// Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed + one cubic correction step.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
+}
+
 __device__ __forceinline__ bool project(const OrthoArgs& a, double x, double y, double z, double* kx, double* ky) {
   // aslam::PinholeCamera::project3: rz = 1/z; (u,v) = (x,y)*rz; distort; k = f*u + c.  Returns the reference's
   // keypoint_visible predicate (ortho-backward-grid.cc:164-171): inside the raster and z > 1e-10
   // (POINT_BEHIND_CAMERA is z < 0, PROJECTION_INVALID is 0 <= z <= 1e-10; both rejected).
-  const double rz = 1.0 / z;
+  const double rz = fast_rcp(z);  // 1.0 / z to <= 1 ulp (z > 1e-10 here)
   double u = x * rz;
   double v = y * rz;
   if (a.dist_type == AMB_DIST_RADTAN) {
@@ -142,17 +154,30 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_const
     bool keep = f < a.n_frames;
     if (keep && a.do_cull) {
       // per-thread frame index: read from global memory (a divergent __constant__ index would serialise)
-      const double* cf = a.cull_data + 6 * static_cast<size_t>(f);
+      const double* cf = a.cull_data + 12 * static_cast<size_t>(f);
       const double dx = sx - __ldg(cf + 0), dy = sy - __ldg(cf + 1), dz = sz - __ldg(cf + 2);
-      const double zp = dx * __ldg(cf + 3) + dy * __ldg(cf + 4) + dz * __ldg(cf + 5);  // along the optical axis
+      const double xp = dx * __ldg(cf + 3) + dy * __ldg(cf + 4) + dz * __ldg(cf + 5);    // x_c of the centre
+      const double yp = dx * __ldg(cf + 6) + dy * __ldg(cf + 7) + dz * __ldg(cf + 8);    // y_c
+      const double zp = dx * __ldg(cf + 9) + dy * __ldg(cf + 10) + dz * __ldg(cf + 11);  // z_c (optical axis)
       const double dd = dx * dx + dy * dy + dz * dz;
+      const double slack = rho + 1e-9 * (fabs(xp) + fabs(yp) + fabs(zp));
       if (zp + rho <= 0.0) {
         keep = false;  // whole sphere behind the camera plane: z_c <= 0 for every landmark
-      } else if (a.cone) {
-        const double perp = sqrt(fmax(dd - zp * zp, 0.0));
-        // distance from the sphere centre to the solid cone {angle to axis <= theta_c} is at least
-        // perp*cos(theta_c) - zp*sin(theta_c)
-        if (perp * a.cos_c - zp * a.sin_c > rho + 1e-9 * (perp + fabs(zp))) keep = false;
+      } else {
+        if (a.cone) {
+          const double perp = sqrt(fmax(dd - zp * zp, 0.0));
+          // distance from the sphere centre to the solid cone {angle to axis <= theta_c} is at least
+          // perp*cos(theta_c) - zp*sin(theta_c)
+          if (perp * a.cos_c - zp * a.sin_c > slack) keep = false;
+        }
+        if (a.rect) {
+          // a landmark with z_c > 0 and u = x_c/z_c > u_hi has x_c - u_hi*z_c > 0: the sphere lies entirely on
+          // that side of the plane through the camera centre iff the centre's value exceeds rho*|normal|
+          if (xp - a.u_hi * zp > slack * a.nu_hi) keep = false;
+          if (a.u_lo * zp - xp > slack * a.nu_lo) keep = false;
+          if (yp - a.v_hi * zp > slack * a.nv_hi) keep = false;
+          if (a.v_lo * zp - yp > slack * a.nv_lo) keep = false;
+        }
       }
     }
     const unsigned int m = __ballot_sync(0xffffffffu, keep);
@@ -175,9 +200,30 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_const
   const double X = __dadd_rn(a.base_x, __dmul_rn(a.res, -static_cast<double>(i)));
   const double Y = __dadd_rn(a.base_y, __dmul_rn(a.res, -static_cast<double>(a.col_begin + jl)));
   const double Z = static_cast<double>(elev);
+  // ---- winner selection: the reference's recurrence  `alpha_f > (double)best_f32  =>  best_f32 = (float)alpha_f`
+  // with alpha = asin(|z|/norm)  (ortho-backward-grid.cc:173-183), evaluated WITHOUT an asin per candidate.
+  // asin is increasing with slope >= 1, so comparing s2 = z^2/norm^2 = sin^2(alpha) decides the comparison
+  // whenever the gap is larger than what the float32 rounding of the running best can hide:
+  //   running best known exactly (layer value b):        ref2 = sin^2(b), band 1e-11
+  //   running best = (float)asin(s_p) of a pending winner: ref2 = s_p^2,  band 2e-7
+  //       (|(float)a - a| <= 6.0e-8 * a <= 9.4e-8;  s2_f - s2_p > 2e-7  =>  s_f - s_p > 1e-7  =>  alpha_f - alpha_p > 1e-7)
+  // Inside the band the decision is made exactly as the reference does (asin of both, float-rounded best).
   float best = a.elevation_angle[cell];
   int best_f = -1;
   double best_kx = 0.0, best_ky = 0.0;
+  bool pending = false;       // best_f won but (float)asin(...) has not been evaluated yet
+  double pend_z = 0.0, pend_n2 = 1.0;
+  double ref2 = 0.0, band = 0.0;
+  if (best > 0.0f) {
+    const double sb = sin(static_cast<double>(best));
+    ref2 = sb * sb;
+    band = 1e-11;
+  } else if (!(best == 0.0f)) {
+    ref2 = 4.0;  // NaN or negative layer value: `alpha > NaN` is never true; a negative one is beaten by anything
+    band = 0.0;
+    if (best < 0.0f) ref2 = -1.0;
+  }
+  double thr_hi = ref2 + band, thr_lo = ref2 - band;
   bool check_failed = false;
 
   for (int l = 0; l < n_list; ++l) {
@@ -189,18 +235,45 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_const
     if (!(zc > 1e-10)) continue;
     double kx, ky;
     if (!project(a, xc, yc, zc, &kx, &ky)) continue;
-    const double norm = sqrt(xc * xc + yc * yc + zc * zc);
-    const double alpha = asin(fabs(zc) / norm);
-    if (!(alpha > 0.0)) check_failed = true;  // reference: CHECK(alpha > 0.0), :178
-    if (alpha > static_cast<double>(best)) {  // :180 — double against the float32 layer value
-      best = static_cast<float>(alpha);       // :181
+    const double z2 = zc * zc;
+    const double n2 = xc * xc + yc * yc + z2;
+    bool win = z2 > thr_hi * n2;
+    if (!win && z2 >= thr_lo * n2) {
+      // inside the band: decide like the reference
+      if (pending) {
+        best = static_cast<float>(asin(pend_z / sqrt(pend_n2)));
+        pending = false;
+      }
+      const double alpha = asin(fabs(zc) / sqrt(n2));
+      if (!(alpha > 0.0)) check_failed = true;  // reference: CHECK(alpha > 0.0), :178
+      if (alpha > static_cast<double>(best)) {  // :180
+        best = static_cast<float>(alpha);       // :181
+        best_f = f;
+        best_kx = kx;
+        best_ky = ky;
+        ref2 = z2 / n2;
+        thr_hi = ref2 + 2e-7;
+        thr_lo = ref2 - 2e-7;
+      }
+    } else if (win) {
+      pending = true;
+      pend_z = zc;  // > 0
+      pend_n2 = n2;
       best_f = f;
       best_kx = kx;
       best_ky = ky;
+      ref2 = z2 / n2;
+      thr_hi = ref2 + 2e-7;
+      thr_lo = ref2 - 2e-7;
     }
   }
-  if (check_failed) atomicExch(a.error_flag, 1u);
   if (best_f < 0) return;
+  if (pending) {
+    const double alpha = asin(pend_z / sqrt(pend_n2));  // asin(fabs(u(2)) / norm_u), :175-177
+    if (!(alpha > 0.0)) check_failed = true;
+    best = static_cast<float>(alpha);
+  }
+  if (check_failed) atomicExch(a.error_flag, 1u);
 
   a.elevation_angle[cell] = best;
   a.observation_index[cell] = static_cast<float>(a.frame_base + best_f);  // :182
@@ -252,7 +325,7 @@ inline V3 qrot(const Quat& q, const V3& v) {
 // Lipschitz bound on the radial polynomial and scan from far off-axis inwards; the first interval that might
 // reach |D| <= Dmax ends the scan.  If even the outermost interval might (fold-back of a non-monotone
 // polynomial, or pure tangential distortion), the cone is disabled and only "behind the camera" culls.
-bool compute_view_cone(const amb_camera& cam, double* cos_c, double* sin_c) {
+bool compute_view_cone(const amb_camera& cam, double* cos_c, double* sin_c, double* tan_c) {
   const double ax = std::max(cam.cu, cam.width - cam.cu) / std::fabs(cam.fu);
   const double ay = std::max(cam.cv, cam.height - cam.cv) / std::fabs(cam.fv);
   const double dmax = std::sqrt(ax * ax + ay * ay) * (1.0 + 1e-9);
@@ -327,7 +400,28 @@ bool compute_view_cone(const amb_camera& cam, double* cos_c, double* sin_c) {
   const double h = std::sqrt(1.0 + rc * rc);
   *cos_c = 1.0 / h;
   *sin_c = rc / h;
+  *tan_c = rc;
   return true;
+}
+
+// Conservative bounds on the UNDISTORTED normalised keypoint (u, v) of any visible ray.  Inside the view cone
+// (r <= rc) the rad-tan model moves a point by at most  E = |k1| rc^3 + |k2| rc^5 + 4 (|p1|+|p2|) rc^2, and a
+// visible ray's distorted keypoint lies in the raster, so  u in [-cu/fu - E, (W-cu)/fu + E]  (same for v).
+bool compute_view_rect(const amb_camera& cam, double rc, double* u_lo, double* u_hi, double* v_lo, double* v_hi) {
+  double E = 0.0;
+  if (cam.dist_type == AMB_DIST_RADTAN) {
+    const double* k = cam.dist;
+    E = std::fabs(k[0]) * rc * rc * rc + std::fabs(k[1]) * std::pow(rc, 5) +
+        4.0 * (std::fabs(k[2]) + std::fabs(k[3])) * rc * rc;
+  } else if (cam.dist_type != AMB_DIST_NONE) {
+    return false;  // equidistant: the cone is the natural bound
+  }
+  E = E * (1.0 + 1e-9) + 1e-12;
+  *u_lo = -cam.cu / cam.fu - E;
+  *u_hi = (cam.width - cam.cu) / cam.fu + E;
+  *v_lo = -cam.cv / cam.fv - E;
+  *v_hi = (cam.height - cam.cv) / cam.fv + E;
+  return cam.fu > 0.0 && cam.fv > 0.0;
 }
 
 }  // namespace
@@ -357,7 +451,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   const V3 r_tmp = qrot(q_B_C, t_C_B);
   const V3 t_B_C = {-r_tmp.x, -r_tmp.y, -r_tmp.z};
   std::vector<FrameConst> fcs(n);
-  std::vector<double> cull(6 * n);
+  std::vector<double> cull(12 * n);
   for (size_t f = 0; f < n; ++f) {
     const double* p = T_G_B + 7 * f;
     const Quat q_G_B = {p[3], p[4], p[5], p[6]};
@@ -374,9 +468,9 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     fc.m[6] = ex.z; fc.m[7] = ey.z; fc.m[8] = ez.z;
     const V3 ti = qrot(qi, t);
     fc.t[0] = -ti.x; fc.t[1] = -ti.y; fc.t[2] = -ti.z;
-    double* cf = &cull[6 * f];
+    double* cf = &cull[12 * f];
     cf[0] = t.x; cf[1] = t.y; cf[2] = t.z;
-    cf[3] = fc.m[6]; cf[4] = fc.m[7]; cf[5] = fc.m[8];
+    for (int k = 0; k < 9; ++k) cf[3 + k] = fc.m[k];
   }
 
   AMB_CUDA(ctx, ctx->frame_table.reserve(n * sizeof(uint8_t*)));
@@ -384,8 +478,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   unsigned int* counters = ctx->counters.as<unsigned int>();
   AMB_CUDA(ctx, cudaMemsetAsync(counters + 8, 0, 4, s));
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, d_images, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
-  AMB_CUDA(ctx, ctx->frame_cull.reserve(6 * n * sizeof(double)));
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull.data(), 6 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  AMB_CUDA(ctx, ctx->frame_cull.reserve(12 * n * sizeof(double)));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull.data(), 12 * n * sizeof(double), cudaMemcpyHostToDevice, s));
 
   OrthoArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -409,10 +503,18 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   a.fu = camera->fu; a.fv = camera->fv; a.cu = camera->cu; a.cv = camera->cv;
   a.d0 = camera->dist[0]; a.d1 = camera->dist[1]; a.d2 = camera->dist[2]; a.d3 = camera->dist[3];
   a.do_cull = ctx->ortho_brute_force ? 0 : 1;
-  double cc = 0.0, sc = 1.0;
-  a.cone = compute_view_cone(*camera, &cc, &sc) ? 1 : 0;
+  double cc = 0.0, sc = 1.0, tc = 0.0;
+  a.cone = compute_view_cone(*camera, &cc, &sc, &tc) ? 1 : 0;
   a.cos_c = cc;
   a.sin_c = sc;
+  a.rect = 0;
+  if (a.cone && compute_view_rect(*camera, tc, &a.u_lo, &a.u_hi, &a.v_lo, &a.v_hi)) {
+    a.rect = 1;
+    a.nu_lo = std::sqrt(1.0 + a.u_lo * a.u_lo);
+    a.nu_hi = std::sqrt(1.0 + a.u_hi * a.u_hi);
+    a.nv_lo = std::sqrt(1.0 + a.v_lo * a.v_lo);
+    a.nv_hi = std::sqrt(1.0 + a.v_hi * a.v_hi);
+  }
 
   const int tiles_i = (a.rows + OTI - 1) / OTI, tiles_j = (a.cols_slab + OTJ - 1) / OTJ;
   ctx->ortho_launches = 0;
@@ -424,7 +526,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.n_frames = static_cast<int>(nf);
     a.frame_base = static_cast<int>(f0);
     a.images = ctx->frame_table.as<const uint8_t*>() + f0;
-    a.cull_data = ctx->frame_cull.as<double>() + 6 * f0;
+    a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
     ortho_kernel<<<tiles_i * tiles_j, kOrthoThreads, 0, s>>>(a);
     ctx->ortho_launches += 1;
   }
