@@ -243,18 +243,40 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(uint4* __restrict__ dat
 __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restrict__ xyz, size_t n, DsmPlan plan,
                                                           unsigned int* __restrict__ G,
                                                           PointRec* __restrict__ rec) {
-  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < n;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const double px = xyz[3 * t + 0] - plan.shift_x;
-    const double py = xyz[3 * t + 1] - plan.shift_y;
-    const double pz = xyz[3 * t + 2];
-    int bi, bj;
-    if (fine_bin(plan, px, py, &bi, &bj)) {
-      const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
-                             static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
-      const unsigned int pos = atomicAdd(&G[b + 1], 1u);
-      store_rec(rec + pos, px, py, pz, static_cast<unsigned long long>(t));
+  // Latency-bound chain per point (load -> atomic with return -> store): keep kBatch points in flight per thread.
+  constexpr int kBatch = 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t t0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t0 < n; t0 += stride * kBatch) {
+    double px[kBatch], py[kBatch], pz[kBatch];
+    unsigned int bucket[kBatch], pos[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const size_t t = t0 + u * stride;
+      if (t < n) {
+        px[u] = xyz[3 * t + 0];
+        py[u] = xyz[3 * t + 1];
+        pz[u] = xyz[3 * t + 2];
+      } else {
+        px[u] = py[u] = pz[u] = __longlong_as_double(0x7ff8000000000000ll);  // NaN: fine_bin rejects it
+      }
     }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      px[u] -= plan.shift_x;
+      py[u] -= plan.shift_y;
+      int bi, bj;
+      bucket[u] = 0xffffffffu;
+      if (fine_bin(plan, px[u], py[u], &bi, &bj))
+        bucket[u] = static_cast<unsigned int>(bi >> plan.Bshift) +
+                    static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (bucket[u] != 0xffffffffu) pos[u] = atomicAdd(&G[bucket[u] + 1], 1u);
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (bucket[u] != 0xffffffffu)
+        store_rec(rec + pos[u], px[u], py[u], pz[u], static_cast<unsigned long long>(t0 + u * stride));
   }
 }
 
@@ -263,6 +285,36 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
 // kernel needs it (the tile kernel orders every cell's points in shared memory); writing 4 bytes per point
 // instead of permuting the 32-byte records keeps this pass at one read of the records.
 // One warp per bucket; every lane ranks its keys against all keys of the bucket (broadcast loads).
+template <int R>
+__device__ __forceinline__ void rank_bucket(const PointRec* __restrict__ rec, unsigned int* __restrict__ order,
+                                            unsigned int* skeys, unsigned int s, unsigned int k, int lane) {
+  // original indices are < 2^32 (n is checked on the host): compare their low words
+  unsigned int key[R], rank[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const unsigned int q = lane + 32u * r;
+    key[r] = q < k ? static_cast<unsigned int>(__ldg(&rec[s + q].idx)) : 0xffffffffu;
+    rank[r] = 0;
+    skeys[q] = key[r];  // slots >= k hold 0xffffffff: never smaller than a real key
+  }
+  __syncwarp();
+  const unsigned int k4 = (k + 3u) >> 2;
+  const uint4* sk4 = reinterpret_cast<const uint4*>(skeys);
+  for (unsigned int q = 0; q < k4; ++q) {
+    const uint4 o = sk4[q];  // broadcast
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      rank[r] += (o.x < key[r] ? 1u : 0u) + (o.y < key[r] ? 1u : 0u) + (o.z < key[r] ? 1u : 0u) +
+                 (o.w < key[r] ? 1u : 0u);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const unsigned int q = lane + 32u * r;
+    if (q < k) order[s + rank[r]] = s + q;
+  }
+}
+
 __global__ void __launch_bounds__(256) dsm_bucket_order_kernel(const unsigned int* __restrict__ G,
                                                                unsigned int n_buckets,
                                                                const PointRec* __restrict__ rec,
@@ -275,32 +327,12 @@ __global__ void __launch_bounds__(256) dsm_bucket_order_kernel(const unsigned in
     const unsigned int s = G[b], e = G[b + 1];
     const unsigned int k = e - s;
     if (k == 0) continue;
-    if (k <= static_cast<unsigned int>(kMaxK)) {
-      // original indices are < 2^32 (n is checked on the host): compare their low words
-      unsigned int key[kSortRegs], rank[kSortRegs];
-#pragma unroll
-      for (int r = 0; r < kSortRegs; ++r) {
-        const unsigned int q = lane + 32u * r;
-        key[r] = q < k ? static_cast<unsigned int>(__ldg(&rec[s + q].idx)) : 0xffffffffu;
-        rank[r] = 0;
-        skeys[warp][q] = key[r];  // slots >= k hold 0xffffffff: never smaller than a real key
-      }
-      __syncwarp();
-      const unsigned int k4 = (k + 3u) >> 2;
-      const uint4* sk4 = reinterpret_cast<const uint4*>(skeys[warp]);
-      for (unsigned int q = 0; q < k4; ++q) {
-        const uint4 o = sk4[q];  // broadcast
-#pragma unroll
-        for (int r = 0; r < kSortRegs; ++r)
-          rank[r] += (o.x < key[r] ? 1u : 0u) + (o.y < key[r] ? 1u : 0u) + (o.z < key[r] ? 1u : 0u) +
-                     (o.w < key[r] ? 1u : 0u);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < kSortRegs; ++r) {
-        const unsigned int q = lane + 32u * r;
-        if (q < k) order[s + rank[r]] = s + q;
-      }
+    if (k <= 32u) {
+      rank_bucket<1>(rec, order, skeys[warp], s, k, lane);
+    } else if (k <= 64u) {
+      rank_bucket<2>(rec, order, skeys[warp], s, k, lane);
+    } else if (k <= static_cast<unsigned int>(kMaxK)) {
+      rank_bucket<kSortRegs>(rec, order, skeys[warp], s, k, lane);
     } else {
       // far denser than the bucket size was chosen for: rank against the keys in global memory
       for (unsigned int q = lane; q < k; q += 32) {

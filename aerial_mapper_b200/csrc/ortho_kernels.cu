@@ -8,7 +8,7 @@
 // (:186-206).  Winner-takes-all with a float-rounded running maximum — a sequential recurrence per cell, so it
 // is evaluated by one thread per cell in frame order; frames are the inner loop, cells the parallel axis.
 //
-// What makes it fast: the reference projects every cell into every frame.  Here a 32x8 cell tile first discards
+// What makes it fast: the reference projects every cell into every frame.  Here a 32x32 cell tile first discards
 // the frames whose view cone cannot contain any of its cells (a provably conservative test, see
 // compute_view_cone), keeps the survivors as an ascending index list in shared memory, and every thread walks
 // that list reading the per-frame constants (R_C_G, t, camera centre) from __constant__ memory — all threads of
@@ -23,8 +23,9 @@ namespace {
 
 constexpr int kMaxFramesPerLaunch = 512;
 constexpr int OTI = 32;  // tile extent along i (rows; contiguous in memory)
-constexpr int OTJ = 8;   // tile extent along j
-constexpr int kOrthoThreads = OTI * OTJ;
+constexpr int OTJ = 32;  // tile extent along j
+constexpr int kOStrip = 4;  // cells per thread (adjacent along j)
+constexpr int kOrthoThreads = OTI * OTJ / kOStrip;
 
 struct FrameConst {
   double m[9];  // R_C_G (row-major): X_c = m * X + t
@@ -67,14 +68,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(r, t, r);
 }
 
+// aslam::PinholeCamera::project3: rz = 1/z; (u,v) = (x,y)*rz; distort; k = f*u + c.  Returns the reference's
+// keypoint_visible predicate (ortho-backward-grid.cc:164-171): inside the raster and z > 1e-10
+// (POINT_BEHIND_CAMERA is z < 0, PROJECTION_INVALID is 0 <= z <= 1e-10; both rejected).
+template <int DIST>
 __device__ __forceinline__ bool project(const OrthoArgs& a, double x, double y, double z, double* kx, double* ky) {
-  // aslam::PinholeCamera::project3: rz = 1/z; (u,v) = (x,y)*rz; distort; k = f*u + c.  Returns the reference's
-  // keypoint_visible predicate (ortho-backward-grid.cc:164-171): inside the raster and z > 1e-10
-  // (POINT_BEHIND_CAMERA is z < 0, PROJECTION_INVALID is 0 <= z <= 1e-10; both rejected).
-  const double rz = fast_rcp(z);  // 1.0 / z to <= 1 ulp (z > 1e-10 here)
+  const double rz = fast_rcp(fmax(z, 1e-300));  // 1.0 / z to <= 1 ulp; z <= 1e-10 is rejected below
   double u = x * rz;
   double v = y * rz;
-  if (a.dist_type == AMB_DIST_RADTAN) {
+  if (DIST == AMB_DIST_RADTAN) {
     const double mx2 = u * u, my2 = v * v, mxy = u * v;
     const double rho2 = mx2 + my2;
     const double rad = a.d0 * rho2 + a.d1 * rho2 * rho2;
@@ -82,7 +84,7 @@ __device__ __forceinline__ bool project(const OrthoArgs& a, double x, double y, 
     const double vn = v + (v * rad + 2.0 * a.d3 * mxy + a.d2 * (rho2 + 2.0 * my2));
     u = un;
     v = vn;
-  } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
+  } else if (DIST == AMB_DIST_EQUIDISTANT) {
     const double r = sqrt(u * u + v * v);
     if (r > 1e-8) {
       const double th = atan(r);
@@ -99,33 +101,57 @@ __device__ __forceinline__ bool project(const OrthoArgs& a, double x, double y, 
          (*ky < static_cast<double>(a.height)) && (z > 1e-10);
 }
 
-__global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_constant__ OrthoArgs a) {
+// X_c = R_C_G X - R_C_G t_G_C for frame f (T_G_C^-1 . landmark, ortho-backward-grid.cc:157-158)
+__device__ __forceinline__ void to_camera(int f, double X, double Y, double Z, double* xc, double* yc, double* zc) {
+  const FrameConst& fc = c_frames[f];
+  *xc = fma(fc.m[1], Y, fma(fc.m[2], Z, fma(fc.m[0], X, fc.t[0])));
+  *yc = fma(fc.m[4], Y, fma(fc.m[5], Z, fma(fc.m[3], X, fc.t[1])));
+  *zc = fma(fc.m[7], Y, fma(fc.m[8], Z, fma(fc.m[6], X, fc.t[2])));
+}
+
+// asin(fabs(u(2)) / norm_u) exactly as the reference evaluates it (ortho-backward-grid.cc:175-177)
+__device__ __forceinline__ double observation_angle(double xc, double yc, double zc) {
+  return asin(fabs(zc) / sqrt(xc * xc + yc * yc + zc * zc));
+}
+
+// One block = one OTI x OTJ cell tile; one thread = a 1 x kOStrip strip of cells (same i, adjacent j): the
+// per-frame constants are fetched once per thread and serve four cells, and the tile's cull list is built once
+// for 1024 cells.
+template <int DIST>
+__global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_constant__ OrthoArgs a) {
   __shared__ unsigned short s_list[kMaxFramesPerLaunch];
   __shared__ float s_red[2][kOrthoThreads / 32];
   __shared__ int s_warp_cnt[kOrthoThreads / 32];
   __shared__ int s_total;
 
-  const int ti = threadIdx.x & 31, tj = threadIdx.x >> 5;
+  const int ti = threadIdx.x & 31, tq = threadIdx.x >> 5;
   const int tiles_i = (a.rows + OTI - 1) / OTI;
   const int i0 = (blockIdx.x % tiles_i) * OTI;
   const int j0 = (blockIdx.x / tiles_i) * OTJ;
-  const int i = i0 + ti, jl = j0 + tj;
-  const bool in_range = (i < a.rows) && (jl < a.cols_slab);
-  const size_t cell = static_cast<size_t>(jl) * a.rows + i;
+  const int i = i0 + ti;
+  const int jl0 = j0 + kOStrip * tq;
 
-  float elev = __int_as_float(0x7fc00000);
-  if (in_range) elev = a.elevation[cell];
-  const bool valid = in_range && !isnan(elev);  // NaN elevation: every comparison is false, cell untouched
-
+  float elev[kOStrip];
+  unsigned int validmask = 0;
+  float zmin = FLT_MAX, zmax = -FLT_MAX;
+#pragma unroll
+  for (int m = 0; m < kOStrip; ++m) {
+    elev[m] = __int_as_float(0x7fc00000);
+    if (i < a.rows && jl0 + m < a.cols_slab) elev[m] = a.elevation[static_cast<size_t>(jl0 + m) * a.rows + i];
+    if (!isnan(elev[m])) {  // NaN elevation: every comparison is false, the cell stays untouched
+      validmask |= 1u << m;
+      zmin = fminf(zmin, elev[m]);
+      zmax = fmaxf(zmax, elev[m]);
+    }
+  }
   // tile elevation range
-  float zmin = valid ? elev : FLT_MAX, zmax = valid ? elev : -FLT_MAX;
   for (int o = 16; o > 0; o >>= 1) {
     zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
     zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
   }
   if (ti == 0) {
-    s_red[0][tj] = zmin;
-    s_red[1][tj] = zmax;
+    s_red[0][tq] = zmin;
+    s_red[1][tq] = zmax;
   }
   if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
@@ -180,12 +206,12 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_const
         }
       }
     }
-    const unsigned int m = __ballot_sync(0xffffffffu, keep);
-    if (ti == 0) s_warp_cnt[tj] = __popc(m);
+    const unsigned int mk = __ballot_sync(0xffffffffu, keep);
+    if (ti == 0) s_warp_cnt[tq] = __popc(mk);
     __syncthreads();
     int before = s_total;
-    for (int w = 0; w < tj; ++w) before += s_warp_cnt[w];
-    if (keep) s_list[before + __popc(m & ((1u << ti) - 1u))] = static_cast<unsigned short>(f);
+    for (int w = 0; w < tq; ++w) before += s_warp_cnt[w];
+    if (keep) s_list[before + __popc(mk & ((1u << ti) - 1u))] = static_cast<unsigned short>(f);
     __syncthreads();
     if (threadIdx.x == 0) {
       int t = s_total;
@@ -195,102 +221,130 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const __grid_const
     __syncthreads();
   }
   const int n_list = s_total;
-  if (!valid || n_list == 0) return;
+  if (!validmask || n_list == 0) return;
 
-  const double X = __dadd_rn(a.base_x, __dmul_rn(a.res, -static_cast<double>(i)));
-  const double Y = __dadd_rn(a.base_y, __dmul_rn(a.res, -static_cast<double>(a.col_begin + jl)));
-  const double Z = static_cast<double>(elev);
   // ---- winner selection: the reference's recurrence  `alpha_f > (double)best_f32  =>  best_f32 = (float)alpha_f`
   // with alpha = asin(|z|/norm)  (ortho-backward-grid.cc:173-183), evaluated WITHOUT an asin per candidate.
   // asin is increasing with slope >= 1, so comparing s2 = z^2/norm^2 = sin^2(alpha) decides the comparison
   // whenever the gap is larger than what the float32 rounding of the running best can hide:
-  //   running best known exactly (layer value b):        ref2 = sin^2(b), band 1e-11
-  //   running best = (float)asin(s_p) of a pending winner: ref2 = s_p^2,  band 2e-7
+  //   running best known exactly (layer value b):          ref2 = sin^2(b), band 1e-11
+  //   running best = (float)asin(s_p) of a pending winner: ref2 = s_p^2,    band 2e-7
   //       (|(float)a - a| <= 6.0e-8 * a <= 9.4e-8;  s2_f - s2_p > 2e-7  =>  s_f - s_p > 1e-7  =>  alpha_f - alpha_p > 1e-7)
   // Inside the band the decision is made exactly as the reference does (asin of both, float-rounded best).
-  float best = a.elevation_angle[cell];
-  int best_f = -1;
-  double best_kx = 0.0, best_ky = 0.0;
-  bool pending = false;       // best_f won but (float)asin(...) has not been evaluated yet
-  double pend_z = 0.0, pend_n2 = 1.0;
-  double ref2 = 0.0, band = 0.0;
-  if (best > 0.0f) {
-    const double sb = sin(static_cast<double>(best));
-    ref2 = sb * sb;
-    band = 1e-11;
-  } else if (!(best == 0.0f)) {
-    ref2 = 4.0;  // NaN or negative layer value: `alpha > NaN` is never true; a negative one is beaten by anything
-    band = 0.0;
-    if (best < 0.0f) ref2 = -1.0;
+  const double X = __dadd_rn(a.base_x, __dmul_rn(a.res, -static_cast<double>(i)));
+  double Y[kOStrip], Z[kOStrip], thr_hi[kOStrip], thr_lo[kOStrip];
+  float best[kOStrip];
+  int best_f[kOStrip];
+  unsigned int pending = 0;  // bit m: best_f[m] won but (float)asin(...) has not been evaluated yet
+#pragma unroll
+  for (int m = 0; m < kOStrip; ++m) {
+    Y[m] = __dadd_rn(a.base_y, __dmul_rn(a.res, -static_cast<double>(a.col_begin + jl0 + m)));
+    Z[m] = static_cast<double>(elev[m]);
+    best[m] = 0.0f;
+    best_f[m] = -1;
+    double ref2 = 4.0, band = 0.0;  // invalid cell: nothing can win
+    if ((validmask >> m) & 1u) {
+      best[m] = a.elevation_angle[static_cast<size_t>(jl0 + m) * a.rows + i];
+      if (best[m] > 0.0f) {
+        const double sb = sin(static_cast<double>(best[m]));
+        ref2 = sb * sb;
+        band = 1e-11;
+      } else if (best[m] == 0.0f) {
+        ref2 = 0.0;  // any visible frame has alpha > 0
+      } else if (best[m] < 0.0f) {
+        ref2 = -1.0;  // a negative layer value is beaten by anything; NaN (ref2 = 4) by nothing
+      }
+    }
+    thr_hi[m] = ref2 + band;
+    thr_lo[m] = ref2 - band;
   }
-  double thr_hi = ref2 + band, thr_lo = ref2 - band;
   bool check_failed = false;
+  unsigned int dirty = 0;  // bit m: a candidate fell inside the band -> redo that cell exactly after the loop
 
+  // Hot loop: straight-line code, four independent dependency chains per thread (one per cell of the strip).
   for (int l = 0; l < n_list; ++l) {
     const int f = s_list[l];
     const FrameConst& fc = c_frames[f];
-    const double xc = fc.m[0] * X + fc.m[1] * Y + fc.m[2] * Z + fc.t[0];
-    const double yc = fc.m[3] * X + fc.m[4] * Y + fc.m[5] * Z + fc.t[1];
-    const double zc = fc.m[6] * X + fc.m[7] * Y + fc.m[8] * Z + fc.t[2];
-    if (!(zc > 1e-10)) continue;
-    double kx, ky;
-    if (!project(a, xc, yc, zc, &kx, &ky)) continue;
-    const double z2 = zc * zc;
-    const double n2 = xc * xc + yc * yc + z2;
-    bool win = z2 > thr_hi * n2;
-    if (!win && z2 >= thr_lo * n2) {
-      // inside the band: decide like the reference
-      if (pending) {
-        best = static_cast<float>(asin(pend_z / sqrt(pend_n2)));
-        pending = false;
-      }
-      const double alpha = asin(fabs(zc) / sqrt(n2));
-      if (!(alpha > 0.0)) check_failed = true;  // reference: CHECK(alpha > 0.0), :178
-      if (alpha > static_cast<double>(best)) {  // :180
-        best = static_cast<float>(alpha);       // :181
-        best_f = f;
-        best_kx = kx;
-        best_ky = ky;
-        ref2 = z2 / n2;
-        thr_hi = ref2 + 2e-7;
-        thr_lo = ref2 - 2e-7;
-      }
-    } else if (win) {
-      pending = true;
-      pend_z = zc;  // > 0
-      pend_n2 = n2;
-      best_f = f;
-      best_kx = kx;
-      best_ky = ky;
-      ref2 = z2 / n2;
-      thr_hi = ref2 + 2e-7;
-      thr_lo = ref2 - 2e-7;
+    const double cx = fma(fc.m[0], X, fc.t[0]);
+    const double cy = fma(fc.m[3], X, fc.t[1]);
+    const double cz = fma(fc.m[6], X, fc.t[2]);
+#pragma unroll
+    for (int m = 0; m < kOStrip; ++m) {
+      const double xc = fma(fc.m[1], Y[m], fma(fc.m[2], Z[m], cx));
+      const double yc = fma(fc.m[4], Y[m], fma(fc.m[5], Z[m], cy));
+      const double zc = fma(fc.m[7], Y[m], fma(fc.m[8], Z[m], cz));
+      double kx, ky;
+      const bool vis = project<DIST>(a, xc, yc, zc, &kx, &ky);
+      const double z2 = zc * zc;
+      const double n2 = fma(xc, xc, fma(yc, yc, z2));
+      const bool win = vis && (z2 > thr_hi[m] * n2);
+      const bool unc = vis && !win && (z2 >= thr_lo[m] * n2);
+      dirty |= (unc ? 1u : 0u) << m;
+      const double ref2 = z2 * fast_rcp(n2);
+      best_f[m] = win ? f : best_f[m];
+      thr_hi[m] = win ? ref2 + 2e-7 : thr_hi[m];
+      thr_lo[m] = win ? ref2 - 2e-7 : thr_lo[m];
+      pending |= (win ? 1u : 0u) << m;
     }
   }
-  if (best_f < 0) return;
-  if (pending) {
-    const double alpha = asin(pend_z / sqrt(pend_n2));  // asin(fabs(u(2)) / norm_u), :175-177
-    if (!(alpha > 0.0)) check_failed = true;
-    best = static_cast<float>(alpha);
+
+  if (dirty) {
+    // Rare (a near-tie within the float32 rounding of the running best): evaluate the reference's recurrence
+    // literally for those cells — asin for every visible frame, float-rounded best (:173-183).
+#pragma unroll
+    for (int m = 0; m < kOStrip; ++m) {  // unrolled: the per-cell arrays must stay in registers
+      if (!((dirty >> m) & 1u)) continue;
+      float b = a.elevation_angle[static_cast<size_t>(jl0 + m) * a.rows + i];
+      int bf = -1;
+      for (int l = 0; l < n_list; ++l) {
+        const int f = s_list[l];
+        double xc, yc, zc, kx, ky;
+        to_camera(f, X, Y[m], Z[m], &xc, &yc, &zc);
+        if (!project<DIST>(a, xc, yc, zc, &kx, &ky)) continue;
+        const double alpha = observation_angle(xc, yc, zc);
+        if (!(alpha > 0.0)) check_failed = true;  // reference: CHECK(alpha > 0.0), :178
+        if (alpha > static_cast<double>(b)) {     // :180
+          b = static_cast<float>(alpha);          // :181
+          bf = f;
+        }
+      }
+      best[m] = b;
+      best_f[m] = bf;
+      pending &= ~(1u << m);
+    }
+  }
+
+#pragma unroll
+  for (int m = 0; m < kOStrip; ++m) {
+    if (best_f[m] < 0) continue;
+    const size_t cell = static_cast<size_t>(jl0 + m) * a.rows + i;
+    // the winner's camera coordinates and keypoint, recomputed (the reference projects a second time too, :186-188)
+    double xc, yc, zc, kx, ky;
+    to_camera(best_f[m], X, Y[m], Z[m], &xc, &yc, &zc);
+    project<DIST>(a, xc, yc, zc, &kx, &ky);
+    if ((pending >> m) & 1u) {
+      const double alpha = observation_angle(xc, yc, zc);
+      if (!(alpha > 0.0)) check_failed = true;
+      best[m] = static_cast<float>(alpha);
+    }
+    a.elevation_angle[cell] = best[m];
+    a.observation_index[cell] = static_cast<float>(a.frame_base + best_f[m]);  // :182
+    // :183 num_observations += num_observations — 0 stays 0, layer untouched.
+    // :186-193 — round half away from zero, clamp to the last row / column.
+    const int py = min(static_cast<int>(round(ky)), a.height - 1);
+    const int px = min(static_cast<int>(round(kx)), a.width - 1);
+    const uint8_t* img = a.images[best_f[m]];
+    const uint8_t* texel = img + static_cast<size_t>(py) * a.row_step + static_cast<size_t>(px) * a.channels;
+    if (a.colored) {
+      // :194-202 + grid_map::colorVectorToValue: cv::Vec3b is (B,G,R); the packed value is 0x00RRGGBB moved as
+      // raw bits (int(float(c/255.0)*255.0f) == c for every byte c; tests/test_oracle_ortho.py checks all 256).
+      const unsigned int b = __ldg(texel), g = __ldg(texel + 1), r = __ldg(texel + 2);
+      a.out_layer[cell] = __uint_as_float((r << 16) | (g << 8) | b);
+    } else {
+      a.out_layer[cell] = static_cast<float>(__ldg(texel));  // :203-206
+    }
   }
   if (check_failed) atomicExch(a.error_flag, 1u);
-
-  a.elevation_angle[cell] = best;
-  a.observation_index[cell] = static_cast<float>(a.frame_base + best_f);  // :182
-  // :183 num_observations += num_observations — 0 stays 0, layer untouched.
-  // :186-193 — round half away from zero, clamp to the last row / column.
-  const int py = min(static_cast<int>(round(best_ky)), a.height - 1);
-  const int px = min(static_cast<int>(round(best_kx)), a.width - 1);
-  const uint8_t* img = a.images[best_f];
-  const uint8_t* texel = img + static_cast<size_t>(py) * a.row_step + static_cast<size_t>(px) * a.channels;
-  if (a.colored) {
-    // :194-202 + grid_map::colorVectorToValue: cv::Vec3b is (B,G,R); the packed value is 0x00RRGGBB moved as
-    // raw bits (int(float(c/255.0)*255.0f) == c for every byte c; tests/test_oracle_ortho.py checks all 256).
-    const unsigned int b = __ldg(texel), g = __ldg(texel + 1), r = __ldg(texel + 2);
-    a.out_layer[cell] = __uint_as_float((r << 16) | (g << 8) | b);
-  } else {
-    a.out_layer[cell] = static_cast<float>(__ldg(texel));  // :203-206
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -527,7 +581,14 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.frame_base = static_cast<int>(f0);
     a.images = ctx->frame_table.as<const uint8_t*>() + f0;
     a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
-    ortho_kernel<<<tiles_i * tiles_j, kOrthoThreads, 0, s>>>(a);
+    const int grid = tiles_i * tiles_j;
+    if (a.dist_type == AMB_DIST_RADTAN) {
+      ortho_kernel<AMB_DIST_RADTAN><<<grid, kOrthoThreads, 0, s>>>(a);
+    } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
+      ortho_kernel<AMB_DIST_EQUIDISTANT><<<grid, kOrthoThreads, 0, s>>>(a);
+    } else {
+      ortho_kernel<AMB_DIST_NONE><<<grid, kOrthoThreads, 0, s>>>(a);
+    }
     ctx->ortho_launches += 1;
   }
   AMB_CUDA(ctx, cudaGetLastError());
