@@ -44,7 +44,8 @@ class Timings(C.Structure):
                 ("dsm_fill_ms", C.c_float), ("dsm_total_ms", C.c_float), ("ortho_h2d_ms", C.c_float),
                 ("ortho_kernel_ms", C.c_float), ("ortho_total_ms", C.c_float),
                 ("dsm_kernel_launches", C.c_int32), ("ortho_kernel_launches", C.c_int32),
-                ("dsm_points_binned", C.c_int64), ("dsm_cells_empty", C.c_int64)]
+                ("dsm_points_binned", C.c_int64), ("dsm_cells_empty", C.c_int64),
+                ("ortho_h2d_bytes", C.c_int64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -135,7 +135,7 @@ void amb_destroy(amb_ctx* ctx) {
   DeviceBuffer* bufs[] = {&ctx->points,  &ctx->records,   &ctx->point_order,
                             &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
                           &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
-                          &ctx->frame_cull};
+                          &ctx->frame_cull, &ctx->frame_rects, &ctx->ortho_pix, &ctx->ortho_bbox};
   for (DeviceBuffer* b : bufs) b->release();
   for (int k = 0; k < EV_COUNT; ++k)
     if (ctx->events[k]) cudaEventDestroy(ctx->events[k]);
@@ -280,7 +280,8 @@ int amb_ortho_process_device(amb_ctx* ctx, const amb_camera* camera, const doubl
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_BEGIN], ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_H2D_END], ctx->stream));
   ctx->ortho_had_h2d = false;
-  int st = ortho_run(ctx, camera, T_G_B, d_images, n, channels, row_step, colored_ortho);
+  ctx->ortho_two_phase = false;
+  int st = ortho_run(ctx, camera, T_G_B, d_images, nullptr, n, channels, row_step, colored_ortho);
   if (st == AMB_OK) AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_END], ctx->stream));
   ctx->ortho_timed = (st == AMB_OK);
   return st;
@@ -293,20 +294,13 @@ int amb_ortho_process(amb_ctx* ctx, const amb_camera* camera, const double* T_G_
   if (!camera || !T_G_B || !images) return AMB_ERR_INVALID_ARGUMENT;
   if (camera->width <= 0 || camera->height <= 0) return AMB_ERR_SIZE_MISMATCH;
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t frame_bytes = static_cast<size_t>(camera->height) * row_step;
-  const size_t frame_pitch = (frame_bytes + 255) & ~static_cast<size_t>(255);
-  AMB_CUDA(ctx, ctx->frames.reserve(frame_pitch * n));
-  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_BEGIN], ctx->stream));
-  std::vector<const uint8_t*> d_ptrs(n);
-  for (size_t f = 0; f < n; ++f) {
+  for (size_t f = 0; f < n; ++f)
     if (!images[f]) return AMB_ERR_INVALID_ARGUMENT;
-    uint8_t* dst = ctx->frames.as<uint8_t>() + f * frame_pitch;
-    AMB_CUDA(ctx, cudaMemcpyAsync(dst, images[f], frame_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    d_ptrs[f] = dst;
-  }
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_BEGIN], ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_H2D_END], ctx->stream));
   ctx->ortho_had_h2d = true;
-  int st = ortho_run(ctx, camera, T_G_B, d_ptrs.data(), n, channels, row_step, colored_ortho);
+  ctx->ortho_two_phase = true;
+  int st = ortho_run(ctx, camera, T_G_B, nullptr, images, n, channels, row_step, colored_ortho);
   if (st != AMB_OK) return st;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_END], ctx->stream));
   ctx->ortho_timed = true;
@@ -348,8 +342,14 @@ int amb_get_timings(amb_ctx* ctx, amb_timings* out) {
     out->dsm_points_binned = c[2];
   }
   if (ctx->ortho_timed) {
-    out->ortho_h2d_ms = ctx->ortho_had_h2d ? ms(EV_ORTHO_BEGIN, EV_ORTHO_H2D_END) : 0.f;
-    out->ortho_kernel_ms = ms(EV_ORTHO_H2D_END, EV_ORTHO_END);
+    if (ctx->ortho_two_phase) {  // select kernel | sub-rectangle copies | texel kernel
+      out->ortho_h2d_ms = ms(EV_ORTHO_SELECT_END, EV_ORTHO_COPY_END);
+      out->ortho_kernel_ms = ms(EV_ORTHO_H2D_END, EV_ORTHO_SELECT_END) + ms(EV_ORTHO_COPY_END, EV_ORTHO_END);
+      out->ortho_h2d_bytes = ctx->ortho_h2d_bytes;
+    } else {
+      out->ortho_h2d_ms = 0.f;
+      out->ortho_kernel_ms = ms(EV_ORTHO_H2D_END, EV_ORTHO_END);
+    }
     out->ortho_total_ms = ms(EV_ORTHO_BEGIN, EV_ORTHO_END);
     out->ortho_kernel_launches = ctx->ortho_launches;
   }

@@ -50,6 +50,8 @@ enum EventId {
   EV_DSM_FILL_END,
   EV_ORTHO_BEGIN,
   EV_ORTHO_H2D_END,
+  EV_ORTHO_SELECT_END,
+  EV_ORTHO_COPY_END,
   EV_ORTHO_END,
   EV_COUNT
 };
@@ -87,7 +89,12 @@ struct amb_ctx {
   // Ortho scratch
   amb::DeviceBuffer frames;       // device copies of the caller's frames (host entry point)
   amb::DeviceBuffer frame_table;  // per-frame device image pointers
-  amb::DeviceBuffer frame_cull;   // per-frame camera centre + optical axis (tile cull test)
+  amb::DeviceBuffer frame_cull;   // per-frame camera centre + R_C_G rows (tile cull test)
+  amb::DeviceBuffer frame_rects;  // host-frame path: per-frame uploaded sub-rectangle
+  amb::DeviceBuffer ortho_pix;    // host-frame path: winner pixel per cell
+  amb::DeviceBuffer ortho_bbox;   // host-frame path: per-frame bounding box of the winners' pixels
+  int64_t ortho_h2d_bytes = 0;
+  bool ortho_two_phase = false;
   bool ortho_brute_force = false;
 
   size_t slab_cells() const { return static_cast<size_t>(geom.rows) * static_cast<size_t>(col_end - col_begin); }
@@ -114,7 +121,7 @@ int ensure_layer(amb_ctx* ctx, int layer);
 int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius, double center_easting,
             double center_northing);
 int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
-              size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
+              const uint8_t* const* h_images, size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
 std::vector<double> dsm_thresholds(int32_t interpolation_radius);
 
 }  // namespace amb

@@ -43,6 +43,8 @@ struct OrthoArgs {
   const uint8_t* const* images;   // device array: frame -> device raster
   const double* cull_data;        // device array [n_frames][12]: camera centre, R_C_G rows (map frame)
   unsigned int* error_flag;
+  unsigned int* pix;              // SELECT mode: per cell (py << 16 | px) of the winner, untouched if not updated
+  int* bbox;                      // SELECT mode: per frame [xmin, ymin, xmax, ymax] of the winners' pixels
   size_t row_step;
   int n_frames, frame_base;       // frames in this launch; index of its first frame within the process() call
   int rows, cols_slab, col_begin;
@@ -117,9 +119,14 @@ __device__ __forceinline__ double observation_angle(double xc, double yc, double
 // One block = one OTI x OTJ cell tile; one thread = a 1 x kOStrip strip of cells (same i, adjacent j): the
 // per-frame constants are fetched once per thread and serve four cells, and the tile's cull list is built once
 // for 1024 cells.
-template <int DIST>
+// SELECT = false: fused kernel, frames resident in HBM, the winner's texel is fetched in the epilogue.
+// SELECT = true:  phase A of the host-frame path: no texel access at all; records the winner's pixel per cell and
+//                 the bounding box of the winners' pixels per frame, so that only those sub-rectangles of the
+//                 host frames have to cross PCIe (phase B: ortho_texel_kernel).
+template <int DIST, bool SELECT>
 __global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_constant__ OrthoArgs a) {
   __shared__ unsigned short s_list[kMaxFramesPerLaunch];
+  __shared__ int s_bbox[SELECT ? 4 * kMaxFramesPerLaunch : 4];
   __shared__ float s_red[2][kOrthoThreads / 32];
   __shared__ int s_warp_cnt[kOrthoThreads / 32];
   __shared__ int s_total;
@@ -154,6 +161,12 @@ __global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_co
     s_red[1][tq] = zmax;
   }
   if (threadIdx.x == 0) s_total = 0;
+  if (SELECT) {
+    for (int e = threadIdx.x; e < 2 * kMaxFramesPerLaunch; e += kOrthoThreads) {
+      s_bbox[e] = 0x7fffffff;                            // xmin, ymin
+      s_bbox[2 * kMaxFramesPerLaunch + e] = -1;          // xmax, ymax
+    }
+  }
   __syncthreads();
   zmin = s_red[0][0];
   zmax = s_red[1][0];
@@ -221,7 +234,8 @@ __global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_co
     __syncthreads();
   }
   const int n_list = s_total;
-  if (!validmask || n_list == 0) return;
+  if (n_list == 0) return;
+  if (!SELECT && !validmask) return;  // (SELECT: every thread reaches the block-wide bbox flush below)
 
   // ---- winner selection: the reference's recurrence  `alpha_f > (double)best_f32  =>  best_f32 = (float)alpha_f`
   // with alpha = asin(|z|/norm)  (ortho-backward-grid.cc:173-183), evaluated WITHOUT an asin per candidate.
@@ -333,18 +347,69 @@ __global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_co
     // :186-193 — round half away from zero, clamp to the last row / column.
     const int py = min(static_cast<int>(round(ky)), a.height - 1);
     const int px = min(static_cast<int>(round(kx)), a.width - 1);
-    const uint8_t* img = a.images[best_f[m]];
-    const uint8_t* texel = img + static_cast<size_t>(py) * a.row_step + static_cast<size_t>(px) * a.channels;
-    if (a.colored) {
-      // :194-202 + grid_map::colorVectorToValue: cv::Vec3b is (B,G,R); the packed value is 0x00RRGGBB moved as
-      // raw bits (int(float(c/255.0)*255.0f) == c for every byte c; tests/test_oracle_ortho.py checks all 256).
-      const unsigned int b = __ldg(texel), g = __ldg(texel + 1), r = __ldg(texel + 2);
-      a.out_layer[cell] = __uint_as_float((r << 16) | (g << 8) | b);
+    if (SELECT) {
+      a.pix[cell] = (static_cast<unsigned int>(py) << 16) | static_cast<unsigned int>(px);
+      const int bf = best_f[m];
+      atomicMin(&s_bbox[bf], px);
+      atomicMin(&s_bbox[kMaxFramesPerLaunch + bf], py);
+      atomicMax(&s_bbox[2 * kMaxFramesPerLaunch + bf], px);
+      atomicMax(&s_bbox[3 * kMaxFramesPerLaunch + bf], py);
     } else {
-      a.out_layer[cell] = static_cast<float>(__ldg(texel));  // :203-206
+      const uint8_t* img = a.images[best_f[m]];
+      const uint8_t* texel = img + static_cast<size_t>(py) * a.row_step + static_cast<size_t>(px) * a.channels;
+      if (a.colored) {
+        // :194-202 + grid_map::colorVectorToValue: cv::Vec3b is (B,G,R); the packed value is 0x00RRGGBB moved as
+        // raw bits (int(float(c/255.0)*255.0f) == c for every byte c; tests/test_oracle_ortho.py checks all 256).
+        const unsigned int b = __ldg(texel), g = __ldg(texel + 1), r = __ldg(texel + 2);
+        a.out_layer[cell] = __uint_as_float((r << 16) | (g << 8) | b);
+      } else {
+        a.out_layer[cell] = static_cast<float>(__ldg(texel));  // :203-206
+      }
     }
   }
   if (check_failed) atomicExch(a.error_flag, 1u);
+  if (SELECT) {
+    __syncthreads();
+    for (int l = threadIdx.x; l < n_list; l += kOrthoThreads) {
+      const int f = s_list[l];
+      if (s_bbox[2 * kMaxFramesPerLaunch + f] >= 0) {
+        int* g = a.bbox + 4 * (a.frame_base + f);
+        atomicMin(g + 0, s_bbox[f]);
+        atomicMin(g + 1, s_bbox[kMaxFramesPerLaunch + f]);
+        atomicMax(g + 2, s_bbox[2 * kMaxFramesPerLaunch + f]);
+        atomicMax(g + 3, s_bbox[3 * kMaxFramesPerLaunch + f]);
+      }
+    }
+  }
+}
+
+// Phase B of the host-frame path: one thread per cell fetches the winner's texel from the uploaded sub-rectangle.
+struct FrameRect {
+  const uint8_t* ptr;  // device copy of rows [y0, y1] x columns [x0, x1] of the frame
+  int x0, y0;
+  int pitch;           // bytes per row of the device copy
+  int pad_;
+};
+
+__global__ void __launch_bounds__(256) ortho_texel_kernel(const unsigned int* __restrict__ pix,
+                                                          const float* __restrict__ observation_index,
+                                                          const FrameRect* __restrict__ rects, float* out_layer,
+                                                          size_t cells, int channels, int colored) {
+  for (size_t cell = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; cell < cells;
+       cell += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const unsigned int p = pix[cell];
+    if (p == 0xffffffffu) continue;  // not updated by this process() call
+    const int f = static_cast<int>(observation_index[cell]);  // index within this call (exact in float32)
+    const FrameRect r = rects[f];
+    const int px = static_cast<int>(p & 0xffffu), py = static_cast<int>(p >> 16);
+    const uint8_t* texel = r.ptr + static_cast<size_t>(py - r.y0) * r.pitch + static_cast<size_t>(px - r.x0) * channels;
+    if (colored) {
+      const unsigned int b = __ldg(texel), g = __ldg(texel + 1), rr = __ldg(texel + 2);
+      out_layer[cell] = __uint_as_float((rr << 16) | (g << 8) | b);
+    } else {
+      out_layer[cell] = static_cast<float>(__ldg(texel));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -480,10 +545,18 @@ bool compute_view_rect(const amb_camera& cam, double rc, double* u_lo, double* u
 
 }  // namespace
 
+// d_images != nullptr: frames resident in HBM -> one fused kernel per chunk of frames.
+// h_images != nullptr: frames in HOST memory -> phase A selects the winners without touching any pixel, the host
+//   reads back the per-frame bounding boxes of the winners' pixels, only those sub-rectangles are copied to the
+//   device (cudaMemcpy2DAsync), phase B fetches the texels.  Same results, a fraction of the PCIe traffic: a cell
+//   is seen by ~8 frames but takes its pixel from one.
 int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
-              size_t n, int32_t channels, size_t row_step, int32_t colored_ortho) {
+              const uint8_t* const* h_images, size_t n, int32_t channels, size_t row_step,
+              int32_t colored_ortho) {
   if (n == 0) return AMB_ERR_EMPTY;  // CHECK(!T_G_Bs.empty()), ortho-backward-grid.cc:225
-  if (!camera || !T_G_B || !d_images) return AMB_ERR_INVALID_ARGUMENT;
+  if (!camera || !T_G_B || (!d_images && !h_images)) return AMB_ERR_INVALID_ARGUMENT;
+  const bool select_only = d_images == nullptr;
+  if (camera->width > 65535 || camera->height > 65535) return AMB_ERR_UNSUPPORTED;
   if (colored_ortho ? channels != 3 : channels != 1) return AMB_ERR_SIZE_MISMATCH;
   if (camera->width <= 0 || camera->height <= 0 || row_step < static_cast<size_t>(camera->width) * channels)
     return AMB_ERR_SIZE_MISMATCH;
@@ -531,7 +604,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   AMB_CUDA(ctx, ctx->counters.reserve(64));
   unsigned int* counters = ctx->counters.as<unsigned int>();
   AMB_CUDA(ctx, cudaMemsetAsync(counters + 8, 0, 4, s));
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, d_images, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
+  if (!select_only)
+    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, d_images, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
   AMB_CUDA(ctx, ctx->frame_cull.reserve(12 * n * sizeof(double)));
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull.data(), 12 * n * sizeof(double), cudaMemcpyHostToDevice, s));
 
@@ -542,6 +616,19 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   a.observation_index = ctx->layers[AMB_LAYER_OBSERVATION_INDEX];
   a.out_layer = ctx->layers[out_layer];
   a.error_flag = counters + 8;
+  std::vector<int> bbox;
+  const size_t cells = ctx->slab_cells();
+  if (select_only) {
+    AMB_CUDA(ctx, ctx->ortho_pix.reserve(cells * sizeof(unsigned int)));
+    AMB_CUDA(ctx, ctx->ortho_bbox.reserve(n * 4 * sizeof(int)));
+    AMB_CUDA(ctx, cudaMemsetAsync(ctx->ortho_pix.ptr, 0xff, cells * sizeof(unsigned int), s));
+    bbox.assign(4 * n, -1);
+    for (size_t f = 0; f < n; ++f) bbox[4 * f + 0] = bbox[4 * f + 1] = 0x7fffffff;
+    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->ortho_bbox.ptr, bbox.data(), bbox.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, s));
+    a.pix = ctx->ortho_pix.as<unsigned int>();
+    a.bbox = ctx->ortho_bbox.as<int>();
+  }
   a.row_step = row_step;
   a.rows = g.rows;
   a.cols_slab = ctx->col_end - ctx->col_begin;
@@ -582,16 +669,68 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.images = ctx->frame_table.as<const uint8_t*>() + f0;
     a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
     const int grid = tiles_i * tiles_j;
-    if (a.dist_type == AMB_DIST_RADTAN) {
-      ortho_kernel<AMB_DIST_RADTAN><<<grid, kOrthoThreads, 0, s>>>(a);
+    if (select_only) {
+      if (a.dist_type == AMB_DIST_RADTAN) {
+        ortho_kernel<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
+      } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
+        ortho_kernel<AMB_DIST_EQUIDISTANT, true><<<grid, kOrthoThreads, 0, s>>>(a);
+      } else {
+        ortho_kernel<AMB_DIST_NONE, true><<<grid, kOrthoThreads, 0, s>>>(a);
+      }
+    } else if (a.dist_type == AMB_DIST_RADTAN) {
+      ortho_kernel<AMB_DIST_RADTAN, false><<<grid, kOrthoThreads, 0, s>>>(a);
     } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
-      ortho_kernel<AMB_DIST_EQUIDISTANT><<<grid, kOrthoThreads, 0, s>>>(a);
+      ortho_kernel<AMB_DIST_EQUIDISTANT, false><<<grid, kOrthoThreads, 0, s>>>(a);
     } else {
-      ortho_kernel<AMB_DIST_NONE><<<grid, kOrthoThreads, 0, s>>>(a);
+      ortho_kernel<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
     }
     ctx->ortho_launches += 1;
   }
   AMB_CUDA(ctx, cudaGetLastError());
+  ctx->ortho_h2d_bytes = 0;
+  if (!select_only) return AMB_OK;
+
+  // ---- host frames: bounding boxes back, sub-rectangles up, texel gather ----
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_SELECT_END], s));
+  AMB_CUDA(ctx, cudaMemcpyAsync(bbox.data(), ctx->ortho_bbox.ptr, bbox.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  AMB_CUDA(ctx, cudaStreamSynchronize(s));
+  std::vector<FrameRect> rects(n);
+  size_t total = 0;
+  for (size_t f = 0; f < n; ++f) {
+    FrameRect& r = rects[f];
+    r.ptr = nullptr;
+    r.x0 = r.y0 = r.pitch = r.pad_ = 0;
+    if (bbox[4 * f + 2] < 0) continue;  // no cell takes its pixel from this frame
+    const int w = bbox[4 * f + 2] - bbox[4 * f + 0] + 1;
+    r.x0 = bbox[4 * f + 0];
+    r.y0 = bbox[4 * f + 1];
+    r.pitch = static_cast<int>((static_cast<size_t>(w) * channels + 255) & ~static_cast<size_t>(255));
+    r.pad_ = bbox[4 * f + 3] - bbox[4 * f + 1] + 1;  // rows
+    total += static_cast<size_t>(r.pitch) * r.pad_;
+  }
+  AMB_CUDA(ctx, ctx->frames.reserve(total + 256));
+  AMB_CUDA(ctx, ctx->frame_rects.reserve(n * sizeof(FrameRect)));
+  size_t off = 0;
+  for (size_t f = 0; f < n; ++f) {
+    FrameRect& r = rects[f];
+    if (bbox[4 * f + 2] < 0) continue;
+    const int w = bbox[4 * f + 2] - r.x0 + 1, h = r.pad_;
+    uint8_t* dst = ctx->frames.as<uint8_t>() + off;
+    const uint8_t* src = h_images[f] + static_cast<size_t>(r.y0) * row_step + static_cast<size_t>(r.x0) * channels;
+    AMB_CUDA(ctx, cudaMemcpy2DAsync(dst, r.pitch, src, row_step, static_cast<size_t>(w) * channels, h,
+                                    cudaMemcpyHostToDevice, s));
+    ctx->ortho_h2d_bytes += static_cast<int64_t>(w) * channels * h;
+    r.ptr = dst;
+    off += static_cast<size_t>(r.pitch) * h;
+    r.pad_ = 0;
+  }
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_rects.ptr, rects.data(), n * sizeof(FrameRect), cudaMemcpyHostToDevice, s));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_COPY_END], s));
+  ortho_texel_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(a.pix, a.observation_index, ctx->frame_rects.as<FrameRect>(),
+                                                    a.out_layer, cells, channels, a.colored);
+  ctx->ortho_launches += 1;
+  AMB_CUDA(ctx, cudaGetLastError());
+  // `rects` is pageable: the async copy above was staged before returning
   return AMB_OK;
 }
 

@@ -95,13 +95,14 @@ typedef struct amb_timings {
   float dsm_gather_ms;   /* tile IDW gather kernel (the dominant DSM kernel) */
   float dsm_fill_ms;     /* expanding-radius hole fill kernel */
   float dsm_total_ms;
-  float ortho_h2d_ms;    /* host->device copy of the frames (host entry point only) */
-  float ortho_kernel_ms; /* project/select/gather kernel(s) */
+  float ortho_h2d_ms;    /* host->device copy of the needed frame sub-rectangles (host entry point only) */
+  float ortho_kernel_ms; /* project/select kernel(s) (+ texel gather kernel on the host entry point) */
   float ortho_total_ms;
   int32_t dsm_kernel_launches;
   int32_t ortho_kernel_launches;
   int64_t dsm_points_binned;  /* points that fell inside the stripe + halo */
-  int64_t dsm_cells_empty;    /* cells that entered the hole-fill pass */
+  int64_t dsm_cells_empty;    /* cells evaluated by the warp-per-cell kernel (empty primary ball / dense tiles) */
+  int64_t ortho_h2d_bytes;    /* host entry point: bytes of frame sub-rectangles actually copied to the device */
 } amb_timings;
 
 typedef struct amb_ctx amb_ctx;
@@ -169,7 +170,9 @@ int amb_dsm_thresholds(int32_t interpolation_radius, double* thresholds, int32_t
  * per row (cv::Mat data/step); channels = 1 (CV_8UC1) or 3 (CV_8UC3, B,G,R byte order).  colored_ortho is
  * ortho::Settings::colored_ortho (ortho-backward-grid.h:39): non-zero writes the packed 0x00RRGGBB bit pattern
  * to `colored_ortho` and requires channels == 3, zero writes the gray value to `ortho` and requires
- * channels == 1.  Reads `elevation`; read-modify-writes `elevation_angle`; writes `observation_index`. */
+ * channels == 1.  Reads `elevation`; read-modify-writes `elevation_angle`; writes `observation_index`.
+ * With HOST frames the winners are selected first (no pixel is touched), and only the bounding rectangle of the
+ * pixels each frame actually contributes is copied to the device before the texels are gathered. */
 int amb_ortho_process(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* images,
                       size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
 /* Same with frames already resident on the context's device: d_images[i] are DEVICE pointers (the pointer
