@@ -150,6 +150,13 @@ class GridMap(object):
             slab = self._slab(name)
             check(lib().amb_download_layer(ctx, LAYER_ID[name], slab.ctypes.data_as(C.c_void_p)), ctx)
 
+    def download_async(self, names=HOT_LAYERS):
+        """Enqueue device->host copies that overlap later work; sync() completes them (pinned layers recommended)."""
+        ctx = self.context()
+        for name in names:
+            slab = self._slab(name)
+            check(lib().amb_download_layer_async(ctx, LAYER_ID[name], slab.ctypes.data_as(C.c_void_p)), ctx)
+
     def to_device(self, device=0, col_range=None, names=HOT_LAYERS):
         """Make the layers device-resident (uploads the current host values once)."""
         self._release()

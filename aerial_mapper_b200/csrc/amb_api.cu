@@ -13,6 +13,14 @@ __global__ void fill_kernel(float* p, size_t n, float v) {
     p[k] = v;
 }
 
+int wait_layer_copy(amb_ctx* ctx, int layer) {
+  if (layer >= 0 && layer < AMB_NUM_LAYERS && ctx->layer_copy_pending[layer]) {
+    AMB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->layer_copy_event[layer], 0));
+    ctx->layer_copy_pending[layer] = false;
+  }
+  return AMB_OK;
+}
+
 int ensure_layer(amb_ctx* ctx, int layer) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS) return AMB_ERR_INVALID_ARGUMENT;
   if (ctx->layers[layer]) return AMB_OK;
@@ -141,6 +149,8 @@ void amb_destroy(amb_ctx* ctx) {
     if (ctx->events[k]) cudaEventDestroy(ctx->events[k]);
   for (int k = 0; k < 2; ++k)
     if (ctx->copy_done[k]) cudaEventDestroy(ctx->copy_done[k]);
+  for (int l = 0; l < AMB_NUM_LAYERS; ++l)
+    if (ctx->layer_copy_event[l]) cudaEventDestroy(ctx->layer_copy_event[l]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -150,6 +160,8 @@ int amb_sync(amb_ctx* ctx) {
   if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (int l = 0; l < AMB_NUM_LAYERS; ++l) ctx->layer_copy_pending[l] = false;
   // Deferred reference CHECKs of the asynchronous `_device` entry points.
   if (ctx->counters.ptr) {
     unsigned int c[16];
@@ -170,6 +182,7 @@ int amb_init_layers(amb_ctx* ctx) {
     // Slabs are allocated lazily and a fresh slab is born with its initial value (ensure_layer), so only the
     // ones that already exist need refilling.
     if (!ctx->layers[l]) continue;
+    wait_layer_copy(ctx, l);
     float v = nan;
     if (l == AMB_LAYER_ORTHO) v = 255.0f;
     if (l == AMB_LAYER_ELEVATION_ANGLE || l == AMB_LAYER_NUM_OBSERVATIONS) v = 0.0f;
@@ -184,6 +197,7 @@ int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab) {
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   int st = ensure_layer(ctx, layer);
   if (st != AMB_OK) return st;
+  wait_layer_copy(ctx, layer);
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->layers[layer], host_slab, ctx->slab_cells() * sizeof(float),
                                 cudaMemcpyHostToDevice, ctx->stream));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -198,6 +212,25 @@ int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab) {
   AMB_CUDA(ctx, cudaMemcpyAsync(host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMB_OK;
+}
+
+int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab) {
+  if (!ctx || !host_slab) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int st = ensure_layer(ctx, layer);
+  if (st != AMB_OK) return st;
+  // ordered after everything enqueued so far on the compute stream, executed on the copy stream so that it
+  // overlaps later kernels and host->device copies (PCIe is full duplex)
+  AMB_CUDA(ctx, cudaEventRecord(ctx->copy_done[0], ctx->stream));
+  AMB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[0], 0));
+  AMB_CUDA(ctx, cudaMemcpyAsync(host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+  // later WRITERS of this layer on the compute stream wait for the copy (wait_layer_copy); readers do not
+  if (!ctx->layer_copy_event[layer])
+    AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->layer_copy_event[layer], cudaEventDisableTiming));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->layer_copy_event[layer], ctx->copy_stream));
+  ctx->layer_copy_pending[layer] = true;
   return AMB_OK;
 }
 

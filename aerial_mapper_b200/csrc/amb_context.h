@@ -66,6 +66,8 @@ struct amb_ctx {
   cudaStream_t copy_stream = nullptr;  // H2D staging overlapped with compute
   cudaEvent_t events[amb::EV_COUNT] = {};
   cudaEvent_t copy_done[2] = {};
+  cudaEvent_t layer_copy_event[AMB_NUM_LAYERS] = {};  // completion of an asynchronous download of that layer
+  bool layer_copy_pending[AMB_NUM_LAYERS] = {};
   bool dsm_timed = false, ortho_timed = false, dsm_had_h2d = false, ortho_had_h2d = false;
   int32_t dsm_launches = 0, ortho_launches = 0;
   std::string last_error;
@@ -116,6 +118,7 @@ inline int fail(amb_ctx* ctx, cudaError_t e, const char* what) {
   } while (0)
 
 int ensure_layer(amb_ctx* ctx, int layer);
+int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for its pending asynchronous download
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius, double center_easting,

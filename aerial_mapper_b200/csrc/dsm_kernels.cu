@@ -781,6 +781,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_r
   if (interpolation_radius < 1 || n >= size_t(0xffffffffu)) return AMB_ERR_INVALID_ARGUMENT;
   int st = ensure_layer(ctx, AMB_LAYER_ELEVATION);
   if (st != AMB_OK) return st;
+  wait_layer_copy(ctx, AMB_LAYER_ELEVATION);
 
   DsmPlan plan;
   std::memset(&plan, 0, sizeof(plan));

@@ -566,6 +566,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   for (int l : need) {
     const int st = ensure_layer(ctx, l);
     if (st != AMB_OK) return st;
+    if (l != AMB_LAYER_ELEVATION) wait_layer_copy(ctx, l);  // written here; elevation is only read
   }
   const amb_geometry& g = ctx->geom;
   cudaStream_t s = ctx->stream;

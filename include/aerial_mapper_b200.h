@@ -141,6 +141,9 @@ int amb_init_layers(amb_ctx* ctx);
  * caller offsets a full-map pointer by rows*col_begin; rows*(col_end-col_begin) floats are moved. */
 int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab);
 int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab);
+/* Same, asynchronous: the copy is ordered after the work enqueued so far and runs on a second stream, so it
+ * overlaps later kernels and host->device copies (use page-locked host memory); amb_sync() completes it. */
+int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab);
 /* Device pointer of a layer slab (allocating it if needed), for device-side consumers (NCCL all-gather of
  * finished stripes, downstream kernels). */
 int amb_layer_device_ptr(amb_ctx* ctx, int layer, float** device_slab);

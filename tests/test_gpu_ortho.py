@@ -229,3 +229,31 @@ def test_property_frame_constant_images_large():
     gm.download(("ortho", "elevation_angle", "observation_index"))
     for k in cull:
         assert np.array_equal(cull[k].view(np.uint32), gm[k].view(np.uint32)), k
+
+
+def test_async_download_overlaps_but_returns_the_same_bits():
+    rows, cols, res = 128, 96, 0.5
+    xyz = synth.point_cloud(30000, 33.0, 25.0, seed=43)
+    camd, poses, imgs = make_inputs(rows, cols, res, 2, 3, 50.0, 0.08, False)
+    outs = []
+    for use_async in (False, True):
+        gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res), pinned=True).getMutable()
+        gm.to_device(0)
+        amb.Dsm(amb.DsmSettings(), gm).process(xyz, gm)
+        if use_async:
+            gm.download_async(("elevation",))
+        amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), gm).process(poses, imgs, gm)
+        if use_async:
+            gm.download(("ortho", "elevation_angle", "observation_index"))
+            gm.sync()
+            # a later writer of the layer waits for the pending copy: run DSM again, the host copy keeps call 1's bits
+            first = gm["elevation"].copy()
+            gm.download_async(("elevation",))
+            amb.Dsm(amb.DsmSettings(), gm).process(xyz + np.array([0.0, 0.0, 5.0]), gm)
+            gm.sync()
+            assert np.array_equal(first.view(np.uint32), gm["elevation"].view(np.uint32))
+        else:
+            gm.download()
+        outs.append({k: gm[k].copy() for k in ("elevation", "ortho", "elevation_angle", "observation_index")})
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k].view(np.uint32), outs[1][k].view(np.uint32)), k
