@@ -72,6 +72,12 @@ SYMBOLS = {
     "amb_layer_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "amb_dsm_process": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double]),
     "amb_dsm_process_device": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double]),
+    "amb_dsm_process_device_ids": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double]),
+    "amb_stripe_y_interval": (C.c_int, [C.POINTER(Geometry), C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]),
+    "amb_dsm_halo_reach": (C.c_double, [C.POINTER(Geometry), C.c_int32]),
+    "amb_dsm_extract_halo": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, _P,
+                                       _P, C.c_uint32, _P]),
     "amb_dsm_enable_debug": (C.c_int, [_P, C.c_int]),
     "amb_dsm_download_debug": (C.c_int, [_P, _P, _P]),
     "amb_dsm_thresholds": (C.c_int, [C.c_int32, _P, C.c_int32]),

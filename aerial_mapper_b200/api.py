@@ -259,16 +259,22 @@ class Dsm(object):
         if not map.is_resident():
             map.download(("elevation",))
 
-    def process_device(self, d_xyz, n, map):
-        """Points already in HBM (device pointer as int); asynchronous — map.sync() before reading results."""
+    def process_device(self, d_xyz, n, map, d_ids=None):
+        """Points already in HBM (device pointer as int); asynchronous — map.sync() before reading results.
+        d_ids: optional device pointer to one uint64 id per point (a sharded cloud: global point ids)."""
         if n == 0:
             log.warning("Passed empty point cloud to DSM module")
             return
         ctx = map.context()
         s = self.settings_
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
-        check(lib().amb_dsm_process_device(ctx, C.c_void_p(int(d_xyz)), int(n), int(s.interpolation_radius),
-                                           float(s.center_easting), float(s.center_northing)), ctx)
+        if d_ids is None:
+            check(lib().amb_dsm_process_device(ctx, C.c_void_p(int(d_xyz)), int(n), int(s.interpolation_radius),
+                                               float(s.center_easting), float(s.center_northing)), ctx)
+        else:
+            check(lib().amb_dsm_process_device_ids(ctx, C.c_void_p(int(d_xyz)), C.c_void_p(int(d_ids)), int(n),
+                                                   int(s.interpolation_radius), float(s.center_easting),
+                                                   float(s.center_northing)), ctx)
 
     def _fetch_debug(self, map):
         if not self.debug:

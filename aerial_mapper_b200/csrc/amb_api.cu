@@ -253,9 +253,51 @@ int amb_dsm_process_device(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t 
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
   ctx->dsm_had_h2d = false;
-  int st = dsm_run(ctx, d_xyz, n, interpolation_radius, center_easting, center_northing);
+  int st = dsm_run(ctx, d_xyz, nullptr, n, interpolation_radius, center_easting, center_northing);
   ctx->dsm_timed = (st == AMB_OK);
   return st;
+}
+
+int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n,
+                               int32_t interpolation_radius, double center_easting, double center_northing) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;
+  if (!d_xyz) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
+  ctx->dsm_had_h2d = false;
+  int st = dsm_run(ctx, d_xyz, reinterpret_cast<const unsigned long long*>(d_ids), n, interpolation_radius,
+                   center_easting, center_northing);
+  ctx->dsm_timed = (st == AMB_OK);
+  return st;
+}
+
+int amb_stripe_y_interval(const amb_geometry* g, int32_t col_begin, int32_t col_end, double* y_lo, double* y_hi) {
+  if (!g || !y_lo || !y_hi || col_begin < 0 || col_end > g->cols || col_begin >= col_end) return AMB_ERR_INVALID_ARGUMENT;
+  // cell column j is centred at base_y - res*j; the stripe [col_begin, col_end) covers (y_lo, y_hi]
+  const double base_y = g->pos_y + (0.5 * g->length_y - 0.5 * g->resolution);
+  *y_hi = base_y - g->resolution * col_begin + 0.5 * g->resolution;
+  *y_lo = base_y - g->resolution * (col_end - 1) - 0.5 * g->resolution;
+  return AMB_OK;
+}
+
+double amb_dsm_halo_reach(const amb_geometry* g, int32_t interpolation_radius) {
+  if (!g || interpolation_radius < 1) return -1.0;
+  const std::vector<double> thr = dsm_thresholds(interpolation_radius);
+  double m = 0.0;
+  for (double t : thr) m = std::max(m, t);
+  return std::sqrt(m) + g->resolution;  // largest retry reach + one cell of slack
+}
+
+int amb_dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n, double y_lo, double y_hi,
+                         double reach, double center_easting, double* d_out_xyz, uint64_t* d_out_ids,
+                         uint32_t capacity, uint32_t* d_count) {
+  if (!ctx || !d_xyz || !d_out_xyz || !d_out_ids || !d_count) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dsm_extract_halo(ctx, d_xyz, reinterpret_cast<const unsigned long long*>(d_ids), n, y_lo, y_hi, reach,
+                          center_easting, d_out_xyz, reinterpret_cast<unsigned long long*>(d_out_ids), capacity,
+                          d_count);
 }
 
 int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpolation_radius,
@@ -269,7 +311,7 @@ int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpola
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->points.ptr, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
   ctx->dsm_had_h2d = true;
-  int st = dsm_run(ctx, ctx->points.as<double>(), n, interpolation_radius, center_easting, center_northing);
+  int st = dsm_run(ctx, ctx->points.as<double>(), nullptr, n, interpolation_radius, center_easting, center_northing);
   ctx->dsm_timed = (st == AMB_OK);
   if (st != AMB_OK) return st;
   return finish_flags(ctx, 1, AMB_ERR_COINCIDENT_POINT);

@@ -121,8 +121,11 @@ int ensure_layer(amb_ctx* ctx, int layer);
 int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for its pending asynchronous download
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
-int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius, double center_easting,
-            double center_northing);
+int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
+            int32_t interpolation_radius, double center_easting, double center_northing);
+int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n, double y_lo,
+                     double y_hi, double reach, double center_easting, double* d_out_xyz,
+                     unsigned long long* d_out_ids, unsigned int capacity, unsigned int* d_count);
 int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
               const uint8_t* const* h_images, size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
 std::vector<double> dsm_thresholds(int32_t interpolation_radius);

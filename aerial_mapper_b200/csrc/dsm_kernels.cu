@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(uint4* __restrict__ dat
 // ---------------------------------------------------------------------------------------------------------------
 // K3: scatter.  G[b + 1] holds start(b) before this kernel; atomicAdd turns it into start(b + 1), i.e.
 // afterwards G[b] = start(b) for b in [0, nbuckets].
-__global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restrict__ xyz, size_t n, DsmPlan plan,
-                                                          unsigned int* __restrict__ G,
+__global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restrict__ xyz,
+                                                          const unsigned long long* __restrict__ ids, size_t n,
+                                                          DsmPlan plan, unsigned int* __restrict__ G,
                                                           PointRec* __restrict__ rec) {
   // Latency-bound chain per point (load -> atomic with return -> store): keep kBatch points in flight per thread.
   constexpr int kBatch = 4;
@@ -275,8 +276,12 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
       if (bucket[u] != 0xffffffffu) pos[u] = atomicAdd(&G[bucket[u] + 1], 1u);
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
-      if (bucket[u] != 0xffffffffu)
-        store_rec(rec + pos[u], px[u], py[u], pz[u], static_cast<unsigned long long>(t0 + u * stride));
+      if (bucket[u] != 0xffffffffu) {
+        // the canonical-order key: position in the caller's array, or the caller's own (global) point id when the
+        // cloud arrives sharded — so that a stripe sees the same order as the undivided map
+        const size_t t = t0 + u * stride;
+        store_rec(rec + pos[u], px[u], py[u], pz[u], ids ? ids[t] : static_cast<unsigned long long>(t));
+      }
   }
 }
 
@@ -774,8 +779,59 @@ inline int round_up(int v, int m) { return ((v + m - 1) / m) * m; }
 
 }  // namespace
 
-int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius, double center_easting,
-            double center_northing) {
+// Points of a sharded cloud that lie within `reach` of the borders of the y-interval (y_lo, y_hi] a rank owns:
+// what its neighbours need for interpolation (the "border halo").  Unordered append (warp-aggregated atomic);
+// order does not matter because every point carries its global id.
+__global__ void __launch_bounds__(256) dsm_halo_kernel(const double* __restrict__ xyz,
+                                                       const unsigned long long* __restrict__ ids, size_t n,
+                                                       double y_lo, double y_hi, double reach, double shift_y,
+                                                       double* __restrict__ out_xyz,
+                                                       unsigned long long* __restrict__ out_ids,
+                                                       unsigned int capacity, unsigned int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n_round = ((n + stride - 1) / stride) * stride;  // whole warps stay converged for the ballot
+  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < n_round; t += stride) {
+    bool take = false;
+    double x = 0, y = 0, z = 0;
+    if (t < n) {
+      x = xyz[3 * t + 0];
+      y = xyz[3 * t + 1];
+      z = xyz[3 * t + 2];
+      const double ys = y - shift_y;
+      take = (ys < y_lo + reach) || (ys > y_hi - reach);
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, take);
+    if (mask) {
+      const int leader = __ffs(mask) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(count, static_cast<unsigned int>(__popc(mask)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (take) {
+        const unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
+        if (slot < capacity) {
+          out_xyz[3 * static_cast<size_t>(slot) + 0] = x;
+          out_xyz[3 * static_cast<size_t>(slot) + 1] = y;
+          out_xyz[3 * static_cast<size_t>(slot) + 2] = z;
+          out_ids[slot] = ids ? ids[t] : static_cast<unsigned long long>(t);
+        }
+      }
+    }
+  }
+}
+
+int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n, double y_lo,
+                     double y_hi, double reach, double center_easting, double* d_out_xyz,
+                     unsigned long long* d_out_ids, unsigned int capacity, unsigned int* d_count) {
+  AMB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned int), ctx->stream));
+  dsm_halo_kernel<<<kNumSMsB200 * 8, 256, 0, ctx->stream>>>(d_xyz, d_ids, n, y_lo, y_hi, reach, center_easting,
+                                                             d_out_xyz, d_out_ids, capacity, d_count);
+  AMB_CUDA(ctx, cudaGetLastError());
+  return AMB_OK;
+}
+
+int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
+            int32_t interpolation_radius, double center_easting, double center_northing) {
   const amb_geometry& g = ctx->geom;
   if (n == 0) return AMB_ERR_EMPTY;
   if (interpolation_radius < 1 || n >= size_t(0xffffffffu)) return AMB_ERR_INVALID_ARGUMENT;
@@ -867,7 +923,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_r
   scan_spine_kernel<<<1, 1024, 0, s>>>(ctx->block_sums.as<unsigned int>(), scan_blocks);
   scan_apply_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(G), n_vec,
                                                 ctx->block_sums.as<unsigned int>());
-  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n, plan, G, rec);
+  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_ids, n, plan, G, rec);
   dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
                                                       ctx->point_order.as<unsigned int>());
   ctx->dsm_launches += 6;

@@ -51,3 +51,76 @@ def unpack_full(gathered, rows, cols, world, n_layers):
                 full[:, c0:c1] = g[r, k, :c1 - c0, :].T
         out.append(full)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sharded point cloud: each rank holds the points of its own stripe; ONE all-gather of the border halos per step.
+def stripe_y_interval(geometry, c0, c1):
+    """(y_lo, y_hi]: the y-range covered by the cells of columns [c0, c1) (amb_stripe_y_interval)."""
+    import ctypes as C
+    from ._lib import check, lib
+    lo, hi = C.c_double(), C.c_double()
+    check(lib().amb_stripe_y_interval(C.byref(geometry), int(c0), int(c1), C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def owner_mask(y_shifted, y_lo, y_hi, rank, world):
+    """Points (by y - center_easting) owned by `rank`: its interval, plus everything beyond the map on the outer
+    ranks (points outside the map still reach the border cells).  Column 0 is the max-y side (grid_map)."""
+    m = (y_shifted > y_lo) & (y_shifted <= y_hi)
+    if rank == 0:
+        m = m | (y_shifted > y_hi)
+    if rank == world - 1:
+        m = m | (y_shifted <= y_lo)
+    return m
+
+
+class HaloExchange(object):
+    """Per-rank state of the border-halo exchange (torch tensors on the rank's device).
+
+    send buffer (float64): [xyz: 3*cap | ids: cap (uint64 bits) | count: 1]; one all-gather fills `gathered`
+    [world, 4*cap + 1]; assemble() lays out the DSM input `big_xyz` / `big_ids` = [all halos | local points] with
+    this rank's own halo slot and every unused slot set to NaN (amb's binning drops NaN points)."""
+
+    def __init__(self, torch, world, rank, cap, local_xyz, local_ids, device):
+        self.torch, self.world, self.rank, self.cap = torch, world, rank, int(cap)
+        n = local_xyz.shape[0]
+        self.n_local = n
+        self.send = torch.empty(4 * self.cap + 1, dtype=torch.float64, device=device)
+        self.gathered = torch.empty((world, 4 * self.cap + 1), dtype=torch.float64, device=device)
+        self.big_xyz = torch.empty((world * self.cap + n, 3), dtype=torch.float64, device=device)
+        self.big_ids = torch.empty(world * self.cap + n, dtype=torch.int64, device=device)
+        self.big_xyz[world * self.cap:] = local_xyz
+        self.big_ids[world * self.cap:] = local_ids
+        self.local_xyz = self.big_xyz[world * self.cap:]
+        self.local_ids = self.big_ids[world * self.cap:]
+        self.n_total = world * self.cap + n
+
+    def extract(self, ctx, y_lo, y_hi, reach, center_easting=0.0):
+        """Fill the send buffer with this rank's border points (hand-written compaction kernel, ctx's stream)."""
+        import ctypes as C
+        from ._lib import check, lib
+        self.send.fill_(float("nan"))
+        self.torch.cuda.current_stream().synchronize()
+        base = self.send.data_ptr()
+        check(lib().amb_dsm_extract_halo(ctx, C.c_void_p(self.local_xyz.data_ptr()),
+                                         C.c_void_p(self.local_ids.data_ptr()), self.n_local, float(y_lo),
+                                         float(y_hi), float(reach), float(center_easting), C.c_void_p(base),
+                                         C.c_void_p(base + 8 * 3 * self.cap), self.cap,
+                                         C.c_void_p(base + 8 * 4 * self.cap)), ctx)
+        check(lib().amb_sync(ctx), ctx)
+
+    def exchange(self, dist):
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.send)  # the one collective of the DSM stage
+
+    def assemble(self):
+        cap, w = self.cap, self.world
+        self.big_xyz[:w * cap] = self.gathered[:, :3 * cap].reshape(w * cap, 3)
+        self.big_ids[:w * cap] = self.gathered[:, 3 * cap:4 * cap].reshape(-1).view(self.torch.int64)
+        self.big_xyz[self.rank * cap:(self.rank + 1) * cap] = float("nan")  # own halo: already among the local points
+        self.torch.cuda.current_stream().synchronize()
+
+    def counts(self):
+        """Halo sizes reported by every rank (host read; > cap means a truncated halo)."""
+        c = self.gathered[:, 4 * self.cap].contiguous().view(self.torch.int64).cpu().numpy()
+        return (c & 0xffffffff).astype(np.int64)

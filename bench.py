@@ -16,9 +16,11 @@ does the whole job; nothing is cached between steps).
 --impl reference times the reference's CPU algorithm (oracle/_ref: its vendored nanoflann compiled verbatim +
 the restated cell loops, parFor over all host threads) on a bounded sample of the same workload.
 
-Multi-GPU (torchrun, one rank per GPU): the map is sharded by contiguous column stripes; points
-and frames are resident on every rank ("broadcast once", outside the timed region); each rank computes its stripe;
-one NCCL all-gather of the finished stripes per step inside the timed region.  Strong scaling: the job is fixed.
+Multi-GPU (torchrun, one rank per GPU): the map is sharded by contiguous column stripes.  The cloud
+arrives sharded the same way (every rank holds the points of its own stripe, with global point ids); frames are
+resident on every rank ("images broadcast once", outside the timed region).  Per step each rank compacts its border
+points (amb_dsm_extract_halo), ONE NCCL all-gather exchanges the halos, then DSM and ortho run on the stripe; the
+result layers stay sharded.  Strong scaling: the job is fixed.
 """
 import argparse
 import json
@@ -205,26 +207,30 @@ def run_ours(args):
     dsm = amb.Dsm(amb.DsmSettings(), gm)
     ortho = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=False), gm)
 
-    slab_tensors = packed = None
+    hx = None
     if world > 1:
-        slab = rows * (c1 - c0)
-        slab_tensors = []
-        for name in layer_names:
-            p = C.c_void_p()
-            amb.check(amb.lib().amb_layer_device_ptr(ctx, amb.LAYER_ID[name], C.byref(p)))
-            slab_tensors.append(cuda_array(torch, p.value, (slab,), device))
-        width = sharding.stripe_width(cols, world)
-        packed = torch.empty((len(layer_names), rows * width), dtype=torch.float32, device=device)
+        # shard the cloud by stripe (setup, outside the timed region): global ids keep the summation order of the
+        # undivided map, so the sharded result is bit-identical to the single-GPU one
+        y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
+        reach = amb.lib().amb_dsm_halo_reach(C.byref(gm.geometry), 1)
+        own = sharding.owner_mask(xyz_d[:, 1], y_lo, y_hi, rank, world)
+        ids_all = torch.arange(n_points, dtype=torch.int64, device=device)
+        cap = int(n_points * (2.0 * reach) / (2.0 * half_y) * 1.5) + 4096
+        hx = sharding.HaloExchange(torch, world, rank, cap, xyz_d[own], ids_all[own], device)
+        del xyz_d, ids_all, own
+        torch.cuda.empty_cache()
 
     def step_resident():
         amb.check(amb.lib().amb_init_layers(ctx), ctx)
-        dsm.process_device(xyz_d.data_ptr(), n_points, gm)
+        if world > 1:
+            hx.extract(ctx, y_lo, y_hi, reach)   # compaction kernel on the library's stream
+            hx.exchange(dist)                    # the one collective of the step (border halos)
+            hx.assemble()
+            dsm.process_device(hx.big_xyz.data_ptr(), hx.n_total, gm, d_ids=hx.big_ids.data_ptr())
+        else:
+            dsm.process_device(xyz_d.data_ptr(), n_points, gm)
         ortho.process_device(poses, img_ptrs, W, gm)
         gm.sync()
-        if world > 1:
-            sharding.pack_slabs(torch, slab_tensors, rows, width, packed)
-            return sharding.all_gather_stripes(torch, dist, packed, world)  # the one collective of the step
-        return None
 
     def barrier():
         torch.cuda.synchronize()
@@ -236,6 +242,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    if world > 1 and (hx.counts() > hx.cap).any():
+        raise SystemExit("bench.py: border halo truncated (capacity %d, counts %s)" % (hx.cap, hx.counts()))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -250,7 +258,7 @@ def run_ours(args):
         bin_ms.append(tm["dsm_bin_ms"])
         fill_ms.append(tm["dsm_fill_ms"])
         ortho_ms.append(tm["ortho_kernel_ms"])
-        launches += tm["dsm_kernel_launches"] + tm["ortho_kernel_launches"] + len(layer_names)
+        launches += tm["dsm_kernel_launches"] + tm["ortho_kernel_launches"] + len(layer_names) + (1 if world > 1 else 0)
     ev1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -268,8 +276,9 @@ def run_ours(args):
     # ---- e2e: host buffers through the public API ----
     e2e = None
     if not args.no_e2e:
-        xyz_h = torch.empty((n_points, 3), dtype=torch.float64, pin_memory=True)
-        xyz_h.copy_(xyz_d)
+        n_host = n_points if world == 1 else hx.n_local
+        xyz_h = torch.empty((n_host, 3), dtype=torch.float64, pin_memory=True)
+        xyz_h.copy_(xyz_d if world == 1 else hx.local_xyz)
         imgs_h = torch.empty((n_frames, H, W), dtype=torch.uint8, pin_memory=True)
         imgs_h.copy_(imgs_d)
         torch.cuda.synchronize()
@@ -285,7 +294,14 @@ def run_ours(args):
 
         def step_e2e():
             amb.check(amb.lib().amb_init_layers(ctx_h), ctx_h)  # AerialGridMap::initialize values, device side
-            dsm_h.process(xyz_np, gmh)            # amb_dsm_process: HOST points -> H2D inside
+            if world > 1:
+                hx.local_xyz.copy_(xyz_h, non_blocking=True)   # this rank's share of the cloud: host -> device
+                hx.extract(ctx_h, y_lo, y_hi, reach)
+                hx.exchange(dist)
+                hx.assemble()
+                dsm_h.process_device(hx.big_xyz.data_ptr(), hx.n_total, gmh, d_ids=hx.big_ids.data_ptr())
+            else:
+                dsm_h.process(xyz_np, gmh)        # amb_dsm_process: HOST points -> H2D inside
             gmh.download_async(("elevation",))    # DSM result starts streaming back while the ortho stage runs
             ortho_h.process(poses, img_np, gmh)   # amb_ortho_process: HOST frames -> needed sub-rectangles H2D
             gmh.download(("ortho", "elevation_angle", "observation_index"))
@@ -302,7 +318,7 @@ def run_ours(args):
         te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = n_points * 24 + int(ortho_h2d) + n_frames * 7 * 8
+        h2d = n_host * 24 + int(ortho_h2d) + n_frames * 7 * 8
         d2h = 4 * slab_bytes
         e2e = {"value": cells / float(te.item()), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
@@ -319,7 +335,8 @@ def run_ours(args):
 
     peak, peak_src = measured_peak_hbm()
     stripe_cells = rows * (c1 - c0)
-    alg_bytes = DSM_BYTES_PER_POINT * n_points + DSM_BYTES_PER_CELL * stripe_cells
+    n_rank_points = n_points if world == 1 else hx.n_total
+    alg_bytes = DSM_BYTES_PER_POINT * n_rank_points + DSM_BYTES_PER_CELL * stripe_cells
     g_ms = float(np.mean(gather_ms))
     achieved = alg_bytes / (g_ms * 1e-3) / 1e9
     traffic = None
@@ -339,7 +356,8 @@ def run_ours(args):
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res), "points": int(n_points),
                       "frames": "%dx %dx%d gray" % (n_frames, W, H), "interpolation_radius": 1,
-                      "sharding": "column stripes x%d, 1 all-gather/step" % world if world > 1 else "single GPU",
+                      "sharding": ("column stripes x%d; cloud sharded by stripe; 1 all-gather of border halos/step; layers "
+                                   "stay sharded" % world) if world > 1 else "single GPU",
                       "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W) / 1e9)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if e2e is not None:

@@ -158,6 +158,23 @@ int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpola
                     double center_easting, double center_northing);
 int amb_dsm_process_device(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t interpolation_radius,
                            double center_easting, double center_northing);
+/* ---- DSM on a cloud that arrives sharded by column stripe (multi-GPU) ----
+ * Every point carries a caller-defined 64-bit id (< 2^32, unique over the whole cloud): it replaces "position in
+ * the array" as the canonical summation-order key, so a stripe computed from {its own points + its neighbours'
+ * border halos} is bit-identical to the same stripe of the undivided map. */
+int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n,
+                               int32_t interpolation_radius, double center_easting, double center_northing);
+/* The y-interval (y_lo, y_hi] covered by the cells of columns [col_begin, col_end) (points are assigned to the
+ * rank whose interval holds y - center_easting), and how far a point can act across a stripe border. */
+int amb_stripe_y_interval(const amb_geometry* geom, int32_t col_begin, int32_t col_end, double* y_lo, double* y_hi);
+double amb_dsm_halo_reach(const amb_geometry* geom, int32_t interpolation_radius);
+/* Compact the points within `reach` of the borders of (y_lo, y_hi] into d_out_* (device buffers of `capacity`
+ * points): the border halo this rank contributes to the single all-gather.  *d_count = number found (may exceed
+ * capacity: then the halo was truncated and the caller must retry with larger buffers).  Asynchronous. */
+int amb_dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n, double y_lo, double y_hi,
+                         double reach, double center_easting, double* d_out_xyz, uint64_t* d_out_ids,
+                         uint32_t capacity, uint32_t* d_count);
+
 /* Ask the next amb_dsm_process* calls to also record, per cell of the slab, the number of neighbours that
  * entered the IDW sum (result_set.size(), dsm.cc:146) and the index k of the threshold lambda_k*radius that
  * produced them (0 = first query succeeded, 1.. = expanding-radius retries dsm.cc:133-144, -1 = cell untouched). */

@@ -233,3 +233,46 @@ def test_property_neighbour_checksum_large():
             d2 = dx * dx + dy * dy
             total += int(((d2 < 1.0) & inside).sum().item())
     assert int(cnt.astype(np.int64).sum()) == total
+
+
+def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map():
+    """every rank holds only the points of its own stripe; the border halos are compacted by
+    amb_dsm_extract_halo and exchanged (here: three ranks simulated one after the other on one GPU)."""
+    import torch
+    from aerial_mapper_b200 import sharding
+    rows, cols, res, world = 150, 200, 0.5, 3
+    xyz_np = synth.point_cloud(120000, rows * res / 2 + 3.0, cols * res / 2 + 3.0, seed=71, holes=5,
+                               hole_sides=(3.0, 12.0))
+    full, _ = gpu_dsm(rows, cols, res, xyz_np)
+    dev = torch.device("cuda:0")
+    xyz = torch.from_numpy(xyz_np).to(dev)
+    ids = torch.arange(xyz.shape[0], dtype=torch.int64, device=dev)
+    gms, exch = [], []
+    for r in range(world):
+        c0, c1 = sharding.stripe_range(cols, r, world)
+        gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+        gm.to_device(0, col_range=(c0, c1), names=("elevation",))
+        y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
+        m = sharding.owner_mask(xyz[:, 1], y_lo, y_hi, r, world)
+        hx = sharding.HaloExchange(torch, world, r, 20000, xyz[m], ids[m], dev)
+        reach = amb.lib().amb_dsm_halo_reach(ctypes_byref(gm.geometry), 1)
+        hx.extract(gm.context(), y_lo, y_hi, reach)
+        gms.append((gm, c0, c1))
+        exch.append(hx)
+    assert sum(h.n_local for h in exch) == xyz.shape[0]          # the stripes partition the cloud
+    gathered = torch.stack([h.send for h in exch])               # what the all-gather would deliver
+    for r, (hx, (gm, c0, c1)) in enumerate(zip(exch, gms)):
+        hx.gathered.copy_(gathered)
+        assert (hx.counts() <= hx.cap).all() and (hx.counts() > 0).all()
+        hx.assemble()
+        d = amb.Dsm(amb.DsmSettings(), gm)
+        d.process_device(hx.big_xyz.data_ptr(), hx.n_total, gm, d_ids=hx.big_ids.data_ptr())
+        gm.sync()
+        gm.download(("elevation",))
+        assert np.array_equal(gm["elevation"][:, c0:c1].view(np.uint32), full["elevation"][:, c0:c1].view(np.uint32))
+    assert np.isnan(full["elevation"]).any()
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
