@@ -273,6 +273,12 @@ int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t
   return st;
 }
 
+int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell) {
+  if (!ctx || !(points_per_cell >= 0.0)) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->dsm_density_hint = points_per_cell;
+  return AMB_OK;
+}
+
 int amb_stripe_y_interval(const amb_geometry* g, int32_t col_begin, int32_t col_end, double* y_lo, double* y_hi) {
   if (!g || !y_lo || !y_hi || col_begin < 0 || col_end > g->cols || col_begin >= col_end) return AMB_ERR_INVALID_ARGUMENT;
   // cell column j is centred at base_y - res*j; the stripe [col_begin, col_end) covers (y_lo, y_hi]

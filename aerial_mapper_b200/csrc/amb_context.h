@@ -84,6 +84,7 @@ struct amb_ctx {
   amb::DeviceBuffer counters;     // small: [0] empty count, [1] error flag, [2] binned points (2 x uint32)
   amb::DeviceBuffer dbg_count;    // int32 per slab cell
   amb::DeviceBuffer dbg_level;    // int8 per slab cell
+  double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;

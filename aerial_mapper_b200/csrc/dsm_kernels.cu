@@ -868,7 +868,12 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
 
   // Bucket edge: a power of two (<= 16 cells) such that a bucket holds a few dozen points at the cloud's average
   // density over the map (the points actually binned may be fewer: that only makes buckets emptier).
-  const double per_cell = static_cast<double>(n) / (static_cast<double>(g.rows) * static_cast<double>(g.cols));
+  // With a sharded cloud `n` is only this rank's share: the caller then states the density of the whole cloud
+  // (amb_dsm_set_density_hint), so that bucket size and stage capacity — which fix the summation orders — are the
+  // same for every sharding of the same job.
+  const double per_cell = ctx->dsm_density_hint > 0.0
+                              ? ctx->dsm_density_hint
+                              : static_cast<double>(n) / (static_cast<double>(g.rows) * static_cast<double>(g.cols));
   int B = 1, shift = 0;
   while (B < 16 && per_cell * (2.0 * B) * (2.0 * B) <= 48.0) {
     B *= 2;

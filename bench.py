@@ -217,6 +217,7 @@ def run_ours(args):
         ids_all = torch.arange(n_points, dtype=torch.int64, device=device)
         cap = int(n_points * (2.0 * reach) / (2.0 * half_y) * 1.5) + 4096
         hx = sharding.HaloExchange(torch, world, rank, cap, xyz_d[own], ids_all[own], device)
+        amb.check(amb.lib().amb_dsm_set_density_hint(ctx, n_points / float(rows * cols)), ctx)
         del xyz_d, ids_all, own
         torch.cuda.empty_cache()
 
@@ -288,6 +289,8 @@ def run_ours(args):
         gmh = gm_h.getMutable()
         gmh.to_device(local_rank, col_range=(c0, c1), names=layer_names)  # layers live in HBM between calls
         ctx_h = gmh.context()
+        if world > 1:
+            amb.check(amb.lib().amb_dsm_set_density_hint(ctx_h, n_points / float(rows * cols)), ctx_h)
         dsm_h = amb.Dsm(amb.DsmSettings(), gmh)
         ortho_h = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=False), gmh)
         slab_bytes = rows * (c1 - c0) * 4

@@ -164,6 +164,11 @@ int amb_dsm_process_device(amb_ctx* ctx, const double* d_xyz, size_t n, int32_t 
  * border halos} is bit-identical to the same stripe of the undivided map. */
 int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n,
                                int32_t interpolation_radius, double center_easting, double center_northing);
+/* Average number of points per grid cell of the WHOLE cloud (n_global / (rows*cols)).  The bucket size and the
+ * shared-memory stage are sized from the density; with a sharded cloud each rank sees only its share, so every
+ * rank passes the same global figure to keep all summation orders — every output bit — independent of the
+ * sharding.  0 (default): derive it from the points passed to each call. */
+int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell);
 /* The y-interval (y_lo, y_hi] covered by the cells of columns [col_begin, col_end) (points are assigned to the
  * rank whose interval holds y - center_easting), and how far a point can act across a stripe border. */
 int amb_stripe_y_interval(const amb_geometry* geom, int32_t col_begin, int32_t col_end, double* y_lo, double* y_hi);

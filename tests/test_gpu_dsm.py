@@ -256,6 +256,7 @@ def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map()
         m = sharding.owner_mask(xyz[:, 1], y_lo, y_hi, r, world)
         hx = sharding.HaloExchange(torch, world, r, 20000, xyz[m], ids[m], dev)
         reach = amb.lib().amb_dsm_halo_reach(ctypes_byref(gm.geometry), 1)
+        amb.check(amb.lib().amb_dsm_set_density_hint(gm.context(), xyz.shape[0] / float(rows * cols)), gm.context())
         hx.extract(gm.context(), y_lo, y_hi, reach)
         gms.append((gm, c0, c1))
         exch.append(hx)
