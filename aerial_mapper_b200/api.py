@@ -394,3 +394,42 @@ class OrthoBackwardGrid(object):
         check(lib().amb_ortho_process_device(ctx, C.byref(self.ncameras_.camera), T.ctypes.data_as(C.c_void_p),
                                              C.cast(ptrs, C.c_void_p), n, 3 if colored else 1, int(row_step),
                                              1 if colored else 0), ctx)
+
+
+class OrthoFromPclSettings(object):
+    """ortho::Settings of ortho-from-pcl.h:28-35 ("next" row N1)."""
+
+    def __init__(self, show_orthomosaic_opencv=False, interpolation_radius=2, use_adaptive_interpolation=False,
+                 save_orthomosaic_jpg=False, orthomosaic_jpg_filename=""):
+        self.show_orthomosaic_opencv = show_orthomosaic_opencv
+        self.interpolation_radius = int(interpolation_radius)
+        self.use_adaptive_interpolation = use_adaptive_interpolation
+        self.save_orthomosaic_jpg = save_orthomosaic_jpg
+        self.orthomosaic_jpg_filename = orthomosaic_jpg_filename
+
+
+class OrthoFromPcl(object):
+    """ortho::OrthoFromPcl (ortho-from-pcl.h:37-52): IDW of point intensities into map['ortho']."""
+
+    def __init__(self, settings):
+        self.settings_ = settings
+
+    def process(self, pointcloud, intensities, map):
+        pc = np.ascontiguousarray(pointcloud, dtype=np.float64)
+        n = pc.size // 3
+        if n == 0:
+            raise AmbError(_lib.AMB_ERR_EMPTY, "CHECK(!pointcloud.empty()) (ortho-from-pcl.cc:23)")
+        if map is None:
+            raise AmbError(_lib.AMB_ERR_INVALID_ARGUMENT, "CHECK(map) (ortho-from-pcl.cc:24)")
+        inten = np.ascontiguousarray(intensities, dtype=np.int32)
+        if inten.size < n:
+            raise AmbError(_lib.AMB_ERR_SIZE_MISMATCH, "CHECK(i < intensities.size()) (ortho-from-pcl.cc:32)")
+        ctx = map.context()
+        s = self.settings_
+        if not map.is_resident():
+            map.upload(("ortho",))
+        check(lib().amb_ortho_from_pcl_process(ctx, pc.ctypes.data_as(C.c_void_p), inten.ctypes.data_as(C.c_void_p),
+                                               n, int(s.interpolation_radius),
+                                               1 if s.use_adaptive_interpolation else 0), ctx)
+        if not map.is_resident():
+            map.download(("ortho",))

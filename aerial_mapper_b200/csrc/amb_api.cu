@@ -140,7 +140,7 @@ void amb_destroy(amb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layers[l]) cudaFree(ctx->layers[l]);
-  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->records,   &ctx->point_order,
+  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->intensities, &ctx->records, &ctx->point_order,
                             &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
                           &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
                           &ctx->frame_cull, &ctx->frame_rects, &ctx->ortho_pix, &ctx->ortho_bbox};
@@ -271,6 +271,45 @@ int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t
                    center_easting, center_northing);
   ctx->dsm_timed = (st == AMB_OK);
   return st;
+}
+
+// ---- OrthoFromPcl ("next" row N1) ----
+int amb_ortho_from_pcl_process_device(amb_ctx* ctx, const double* d_xyz, const int32_t* d_intensities, size_t n,
+                                      int32_t interpolation_radius, int32_t use_adaptive_interpolation) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;  // CHECK(!pointcloud.empty()), ortho-from-pcl.cc:23
+  if (!d_xyz || !d_intensities) return AMB_ERR_INVALID_ARGUMENT;
+  if (use_adaptive_interpolation) return AMB_ERR_UNSUPPORTED;  // unbounded 10^k radius growth: not on this path
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
+  ctx->dsm_had_h2d = false;
+  int st = dsm_run(ctx, d_xyz, nullptr, n, interpolation_radius, 0.0, 0.0, 1, d_intensities);
+  ctx->dsm_timed = (st == AMB_OK);
+  return st;
+}
+
+int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* intensities, size_t n,
+                               int32_t interpolation_radius, int32_t use_adaptive_interpolation) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;
+  if (!xyz || !intensities) return AMB_ERR_INVALID_ARGUMENT;
+  if (use_adaptive_interpolation) return AMB_ERR_UNSUPPORTED;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  AMB_CUDA(ctx, ctx->points.reserve(n * 3 * sizeof(double)));
+  AMB_CUDA(ctx, ctx->intensities.reserve(n * sizeof(int32_t)));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->points.ptr, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->intensities.ptr, intensities, n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
+  ctx->dsm_had_h2d = true;
+  int st = dsm_run(ctx, ctx->points.as<double>(), nullptr, n, interpolation_radius, 0.0, 0.0, 1,
+                   ctx->intensities.as<int>());
+  ctx->dsm_timed = (st == AMB_OK);
+  if (st != AMB_OK) return st;
+  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMB_OK;
 }
 
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell) {

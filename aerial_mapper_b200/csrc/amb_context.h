@@ -76,6 +76,7 @@ struct amb_ctx {
 
   // DSM scratch
   amb::DeviceBuffer points;       // device copy of the caller's xyz (host entry point)
+  amb::DeviceBuffer intensities;  // device copy of the caller's intensities (OrthoFromPcl host entry point)
   amb::DeviceBuffer records;      // bucket-sorted 32-byte point records
   amb::DeviceBuffer point_order;  // uint32 per record: canonical (original-index) visiting order inside a bucket
   amb::DeviceBuffer bin_starts;   // uint32 G[nb + 2]
@@ -123,7 +124,8 @@ int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for it
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
-            int32_t interpolation_radius, double center_easting, double center_northing);
+            int32_t interpolation_radius, double center_easting, double center_northing, int mode = 0,
+            const int* d_intensities = nullptr);
 int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n, double y_lo,
                      double y_hi, double reach, double center_easting, double* d_out_xyz,
                      unsigned long long* d_out_ids, unsigned int capacity, unsigned int* d_count);

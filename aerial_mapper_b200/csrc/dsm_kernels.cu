@@ -76,6 +76,8 @@ struct DsmPlan {
   int KR, KC;     // bucket grid
   int gj0;        // global column of bin column 0 (a multiple of TJ minus Pa: tiles align to GLOBAL columns)
   int tile_j0;    // global tile index of the first tile column of this stripe
+  int mode;       // 0: dsm::Dsm (retry thresholds, coincident point = error); 1: ortho::OrthoFromPcl (no retry,
+                  //    a zero-distance point is a "perfect match", ortho-from-pcl.cc:90-96)
   double base_x, base_y;  // cell centre of index 0: pos + (0.5*length - 0.5*res)   (grid_map getPosition)
   double res, inv_res;
   double shift_x, shift_y;  // dsm.cc:42-43: x -= center_northing, y -= center_easting
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(uint4* __restrict__ dat
 // K3: scatter.  G[b + 1] holds start(b) before this kernel; atomicAdd turns it into start(b + 1), i.e.
 // afterwards G[b] = start(b) for b in [0, nbuckets].
 __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restrict__ xyz,
+                                                          const int* __restrict__ intensities,
                                                           const unsigned long long* __restrict__ ids, size_t n,
                                                           DsmPlan plan, unsigned int* __restrict__ G,
                                                           PointRec* __restrict__ rec) {
@@ -256,7 +259,8 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
       if (t < n) {
         px[u] = xyz[3 * t + 0];
         py[u] = xyz[3 * t + 1];
-        pz[u] = xyz[3 * t + 2];
+        // OrthoFromPcl interpolates the intensities: z = double(intensities[i]) (ortho-from-pcl.cc:33)
+        pz[u] = intensities ? static_cast<double>(intensities[t]) : xyz[3 * t + 2];
       } else {
         px[u] = py[u] = pz[u] = __longlong_as_double(0x7ff8000000000000ll);  // NaN: fine_bin rejects it
       }
@@ -445,27 +449,29 @@ __device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherAr
     const bool valid = (cellmask >> m) & 1u;
     const size_t cell = static_cast<size_t>(jl0 + m) * plan.rows + i;
     const bool has = den[m] > 0.0 || den[m] != den[m];  // any hit adds a positive weight (NaN: coincident point)
+    // d2 == 0 (a point exactly on the cell centre) is the only way a weight becomes inf/NaN: any d2 > 0 is
+    // >= 1e-26 for metre-scale coordinates.  Dsm: reference CHECK(distances[i] > 0.0) aborts (dsm.cc:165).
+    // OrthoFromPcl: "perfect match" (ortho-from-pcl.cc:90-96) — resolved by the warp-per-cell kernel.
+    const bool zero_dist = has && !(den[m] < DBL_MAX);
+    const bool to_cell_kernel = valid && (plan.mode == 0 ? !has : zero_dist);
     if (valid) {
-      if (has) {
-        // d2 == 0 (a point exactly on the cell centre: reference CHECK(distances[i] > 0.0) aborts, dsm.cc:165)
-        // is the only way a weight becomes inf/NaN: any d2 > 0 is >= 1e-26 for metre-scale coordinates.
-        if (!(den[m] < DBL_MAX)) coincident = true;
+      if (zero_dist && plan.mode == 0) coincident = true;
+      if (has && !(zero_dist && plan.mode == 1))
         args.elevation[cell] = __double2float_rn(__ddiv_rn(num[m], den[m]));  // dsm.cc:171-172
-      }
       if (DEBUG) {
         args.dbg_count[cell] = cnt[m];
         args.dbg_level[cell] = has ? 0 : -1;
       }
     }
-    // cells the primary threshold left empty go to the retry pass: one atomic per warp
-    const bool is_empty = valid && !has;
-    const unsigned int mask = __ballot_sync(0xffffffffu, is_empty);
+    // cells for the warp-per-cell pass (Dsm: empty primary ball -> retry thresholds): one atomic per warp
+    const unsigned int mask = __ballot_sync(0xffffffffu, to_cell_kernel);
     if (mask) {
       const int leader = __ffs(mask) - 1;
       unsigned int base = 0;
       if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (is_empty) args.cell_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
+      if (to_cell_kernel)
+        args.cell_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
     }
   }
   if (coincident) atomicExch(&args.counters[1], 1u);
@@ -715,6 +721,8 @@ __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ D
     double num = 0.0, den = 0.0;
     int cnt = 0;
     bool coincident = false;
+    unsigned long long match_idx = ~0ull;  // OrthoFromPcl: zero-distance point with the smallest id
+    double match_z = 0.0;
     for (int kj = kbj0; kj <= kbj1; ++kj) {
       const size_t row = static_cast<size_t>(kj) * plan.KR;
       const unsigned int a = args.G[row + kbi0];
@@ -728,10 +736,18 @@ __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ D
         if (d2 < thr) {
           const double pz = __ldg(reinterpret_cast<const double*>(pr) + 2);
           ++cnt;
-          const double w = fast_rcp(d2);
-          num = fma(pz, w, num);
-          den += w;
-          coincident |= !(d2 > 0.0);
+          if (d2 > 0.0) {
+            const double w = fast_rcp(d2);
+            num = fma(pz, w, num);
+            den += w;
+          } else {
+            coincident = true;
+            const unsigned long long id = __ldg(&pr->idx);
+            if (id < match_idx) {
+              match_idx = id;
+              match_z = pz;
+            }
+          }
         }
       }
     }
@@ -739,11 +755,19 @@ __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ D
       num += __shfl_xor_sync(0xffffffffu, num, o);
       den += __shfl_xor_sync(0xffffffffu, den, o);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      const unsigned long long oi = __shfl_xor_sync(0xffffffffu, match_idx, o);
+      const double oz = __shfl_xor_sync(0xffffffffu, match_z, o);
+      if (oi < match_idx) {
+        match_idx = oi;
+        match_z = oz;
+      }
     }
     coincident = __any_sync(0xffffffffu, coincident);
     if (lane == 0) {
-      if (coincident) atomicExch(&args.counters[1], 1u);
-      args.elevation[cell] = __double2float_rn(__ddiv_rn(num, den));
+      if (coincident && plan.mode == 0) atomicExch(&args.counters[1], 1u);
+      // OrthoFromPcl perfect match: numerator = that height, denominator = 1 (ortho-from-pcl.cc:90-96)
+      const double value = (coincident && plan.mode == 1) ? match_z : __ddiv_rn(num, den);
+      args.elevation[cell] = __double2float_rn(value);
       if (args.dbg_count) {
         args.dbg_count[cell] = cnt;
         args.dbg_level[cell] = static_cast<signed char>(level);
@@ -831,17 +855,23 @@ int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long
 }
 
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
-            int32_t interpolation_radius, double center_easting, double center_northing) {
+            int32_t interpolation_radius, double center_easting, double center_northing, int mode,
+            const int* d_intensities) {
   const amb_geometry& g = ctx->geom;
   if (n == 0) return AMB_ERR_EMPTY;
   if (interpolation_radius < 1 || n >= size_t(0xffffffffu)) return AMB_ERR_INVALID_ARGUMENT;
-  int st = ensure_layer(ctx, AMB_LAYER_ELEVATION);
+  const int out_layer = mode == 1 ? AMB_LAYER_ORTHO : AMB_LAYER_ELEVATION;  // ortho-from-pcl.cc:51 / dsm.cc:116
+  int st = ensure_layer(ctx, out_layer);
   if (st != AMB_OK) return st;
-  wait_layer_copy(ctx, AMB_LAYER_ELEVATION);
+  wait_layer_copy(ctx, out_layer);
 
   DsmPlan plan;
   std::memset(&plan, 0, sizeof(plan));
-  const std::vector<double> thr = dsm_thresholds(interpolation_radius);
+  plan.mode = mode;
+  // Dsm: the retry thresholds of dsm.cc:133-144.  OrthoFromPcl without adaptive interpolation: the one query of
+  // ortho-from-pcl.cc:57-60.
+  const std::vector<double> thr = mode == 1 ? std::vector<double>(1, static_cast<double>(interpolation_radius))
+                                            : dsm_thresholds(interpolation_radius);
   if (thr.size() > static_cast<size_t>(kMaxThresholds)) return AMB_ERR_UNSUPPORTED;
   double thr_max = 0.0;
   for (size_t k = 0; k < thr.size(); ++k) {
@@ -928,7 +958,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   scan_spine_kernel<<<1, 1024, 0, s>>>(ctx->block_sums.as<unsigned int>(), scan_blocks);
   scan_apply_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(G), n_vec,
                                                 ctx->block_sums.as<unsigned int>());
-  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_ids, n, plan, G, rec);
+  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_intensities, d_ids, n, plan, G, rec);
   dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
                                                       ctx->point_order.as<unsigned int>());
   ctx->dsm_launches += 6;
@@ -954,7 +984,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   GatherArgs ga;
   ga.G = G;
   ga.rec = rec;
-  ga.elevation = ctx->layers[AMB_LAYER_ELEVATION];
+  ga.elevation = ctx->layers[out_layer];
   ga.cell_list = ctx->empty_cells.as<unsigned int>();
   ga.counters = counters;
   ga.dbg_count = ctx->dsm_debug ? ctx->dbg_count.as<int>() : nullptr;

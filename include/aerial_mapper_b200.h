@@ -189,6 +189,17 @@ int amb_dsm_download_debug(amb_ctx* ctx, int32_t* neighbour_count, int8_t* thres
  * recurrence.  Returns the count (<= capacity) or a negative status. */
 int amb_dsm_thresholds(int32_t interpolation_radius, double* thresholds, int32_t capacity);
 
+/* ---- "next" row N1: ortho::OrthoFromPcl::process (aerial_mapper_ortho/src/ortho-from-pcl.cc:20-113) ----
+ * IDW of point INTENSITIES into the `ortho` layer: the DSM kernels with z = double(intensities[i]), one radius query
+ * (ortho::Settings::interpolation_radius of ortho-from-pcl.h:28-35, default 2, squared metres), no centre shift, and
+ * a zero-distance point taken as a "perfect match" (:90-96) instead of a CHECK failure.  Cells without a neighbour
+ * keep their value.  use_adaptive_interpolation != 0 (the 10^k radius growth of :63-72, off in the demo's flag
+ * file) returns AMB_ERR_UNSUPPORTED. */
+int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* intensities, size_t n,
+                               int32_t interpolation_radius, int32_t use_adaptive_interpolation);
+int amb_ortho_from_pcl_process_device(amb_ctx* ctx, const double* d_xyz, const int32_t* d_intensities, size_t n,
+                                      int32_t interpolation_radius, int32_t use_adaptive_interpolation);
+
 /* ---- Orthomosaic: ortho::OrthoBackwardGrid::process (ortho-backward-grid.cc:223-239) ---- */
 /* T_G_B: n poses, 7 doubles each in the order of the reference's pose files: x y z qw qx qy qz
  * (aerial-mapper-io.cc:110).  images: n host pointers to H x W x channels uint8 rasters with `row_step` bytes

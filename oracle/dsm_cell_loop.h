@@ -101,5 +101,57 @@ int runDsmCellLoop(const amb_geometry& g, float* elevation, const std::vector<Ds
   return status.load();
 }
 
+/* ortho::OrthoFromPcl::process cell loop (ortho-from-pcl.cc:52-108).  pts[i].z holds double(intensities[i]). */
+template <typename Searcher>
+int runOrthoFromPclCellLoop(const amb_geometry& g, float* ortho, const std::vector<DsmPoint>& pts,
+                            const Searcher& searcher, int32_t interpolation_radius, bool adaptive,
+                            int32_t num_threads, int64_t cell_begin, int64_t cell_end) {
+  const int rows = g.rows;
+  auto cells = [&](int64_t lo, int64_t hi) {
+    std::vector<std::pair<int, double> > indices_dists;
+    for (int64_t k = cell_begin + lo; k < cell_begin + hi; ++k) {
+      const int i = static_cast<int>(k % rows);
+      const int j = static_cast<int>(k / rows);
+      double qx, qy;
+      cellPosition(g, i, j, &qx, &qy);                                                      /* :53-54 */
+      searcher.search(static_cast<double>(interpolation_radius), qx, qy, &indices_dists);  /* :58-61 */
+      if (adaptive) { /* :63-72 — int lambda = 10; lambda *= 10 (unbounded in the reference) */
+        long long lambda = 10;
+        while (indices_dists.size() == 0u && lambda < (1ll << 50)) {
+          searcher.search(static_cast<double>(lambda * interpolation_radius), qx, qy, &indices_dists);
+          lambda *= 10;
+        }
+      }
+      if (indices_dists.size() > 0u) { /* :73-105 */
+        double idw_numerator = 0.0;
+        double idw_denominator = 0.0;
+        bool idw_perfect_match = false;
+        for (const std::pair<int, double>& s : indices_dists) {
+          const double distance = s.second;
+          const double height = pts[s.first].z;
+          if (distance == 0.0) { /* perfect match, no interpolation needed (:90-96) */
+            idw_numerator = height;
+            idw_denominator = 1.0;
+            idw_perfect_match = true;
+          }
+          if (!idw_perfect_match) {
+            idw_numerator += height / distance;
+            idw_denominator += 1.0 / distance;
+          }
+        }
+        const double idw_height = idw_numerator / idw_denominator;
+        ortho[k] = static_cast<float>(idw_height); /* layer_ortho(x, y) = idw_height, :104 */
+      }
+    }
+  };
+  const int64_t n_cells = cell_end - cell_begin;
+  if (num_threads <= 0) {
+    cells(0, n_cells); /* the reference loop is single-threaded */
+  } else {
+    parFor(n_cells, cells, resolveThreads(num_threads));
+  }
+  return AMB_OK;
+}
+
 }  // namespace ambo
 #endif

@@ -118,4 +118,28 @@ extern "C" int ambo_dsm_process(const amb_geometry* geom, float* elevation, cons
   return st;
 }
 
+extern "C" int ambo_ortho_from_pcl_process(const amb_geometry* geom, float* ortho, const double* xyz,
+                                           const int32_t* intensities, size_t n, int32_t interpolation_radius,
+                                           int32_t use_adaptive_interpolation, int32_t num_threads,
+                                           int64_t cell_begin, int64_t cell_end, double* seconds) {
+  if (!geom || !ortho || geom->rows <= 0 || geom->cols <= 0) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY; /* CHECK(!pointcloud.empty()), ortho-from-pcl.cc:23 */
+  if (!xyz || !intensities || interpolation_radius < 1) return AMB_ERR_INVALID_ARGUMENT;
+  if (use_adaptive_interpolation) return AMB_ERR_UNSUPPORTED; /* unbounded radius: nanoflann back end only */
+  const int64_t total = static_cast<int64_t>(geom->rows) * geom->cols;
+  if (cell_begin < 0 || cell_end > total || cell_begin > cell_end) return AMB_ERR_SIZE_MISMATCH;
+  const double t0 = ambo::now();
+  std::vector<DsmPoint> pts(n);
+  for (size_t i = 0; i < n; ++i) { /* ortho-from-pcl.cc:29-34: no centre shift, z = double(intensity) */
+    pts[i].x = xyz[3 * i + 0];
+    pts[i].y = xyz[3 * i + 1];
+    pts[i].z = static_cast<double>(intensities[i]);
+  }
+  BucketSearcher searcher(pts, *geom, static_cast<double>(interpolation_radius));
+  const int st = ambo::runOrthoFromPclCellLoop(*geom, ortho, pts, searcher, interpolation_radius, false,
+                                               num_threads, cell_begin, cell_end);
+  if (seconds) seconds[0] = ambo::now() - t0;
+  return st;
+}
+
 extern "C" int ambo_hardware_concurrency(void) { return static_cast<int>(ambo::resolveThreads(0)); }

@@ -58,6 +58,10 @@ _DSM_ARGS = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32,
              C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
 
 
+_PCL_ARGS = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32,
+             C.c_int64, C.c_int64, C.c_void_p]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -70,6 +74,8 @@ def lib():
                                          C.c_int32, C.c_size_t, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                          C.c_void_p]
         L.ambo_ortho_process.restype = C.c_int
+        L.ambo_ortho_from_pcl_process.argtypes = _PCL_ARGS
+        L.ambo_ortho_from_pcl_process.restype = C.c_int
         L.ambo_project3.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p]
         L.ambo_project3.restype = C.c_int
         L.ambo_transform_to_camera.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]
@@ -96,6 +102,8 @@ def ref():
         L = C.CDLL(_REF_PATH)
         L.ambo_ref_dsm_process.argtypes = _DSM_ARGS
         L.ambo_ref_dsm_process.restype = C.c_int
+        L.ambo_ref_ortho_from_pcl_process.argtypes = _PCL_ARGS
+        L.ambo_ref_ortho_from_pcl_process.restype = C.c_int
         _ref = L
     return _ref
 
@@ -142,6 +150,21 @@ def dsm_process(geom, elevation, xyz, radius=1, center_easting=0.0, center_north
         cnt = cnt.reshape((geom.rows, geom.cols), order="F")
         lvl = lvl.reshape((geom.rows, geom.cols), order="F")
     return st, cnt, lvl, sec
+
+
+def ortho_from_pcl_process(geom, ortho, xyz, intensities, radius=2, adaptive=False, num_threads=0, cell_range=None,
+                           use_ref=False):
+    """Oracle OrthoFromPcl on `ortho` (float32 F-order rows x cols, modified in place).  Returns status."""
+    assert ortho.dtype == np.float32 and ortho.flags.f_contiguous and ortho.shape == (geom.rows, geom.cols)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    inten = np.ascontiguousarray(intensities, dtype=np.int32)
+    n = xyz.size // 3
+    assert inten.size >= n
+    total = geom.rows * geom.cols
+    lo, hi = (0, total) if cell_range is None else cell_range
+    fn = ref().ambo_ref_ortho_from_pcl_process if use_ref else lib().ambo_ortho_from_pcl_process
+    return fn(C.byref(geom), _ptr(ortho), _ptr(xyz), _ptr(inten), n, int(radius), 1 if adaptive else 0,
+              int(num_threads), lo, hi, None)
 
 
 def ortho_process(geom, layers, camera, T_G_B, images, colored=False, num_threads=0, cell_range=None):

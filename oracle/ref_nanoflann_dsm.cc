@@ -90,3 +90,31 @@ extern "C" int ambo_ref_dsm_process(const amb_geometry* geom, float* elevation, 
   }
   return st;
 }
+
+extern "C" int ambo_ref_ortho_from_pcl_process(const amb_geometry* geom, float* ortho, const double* xyz,
+                                               const int32_t* intensities, size_t n,
+                                               int32_t interpolation_radius, int32_t use_adaptive_interpolation,
+                                               int32_t num_threads, int64_t cell_begin, int64_t cell_end,
+                                               double* seconds) {
+  if (!geom || !ortho || geom->rows <= 0 || geom->cols <= 0) return AMB_ERR_INVALID_ARGUMENT;
+  if (n == 0) return AMB_ERR_EMPTY;
+  if (!xyz || !intensities || interpolation_radius < 1) return AMB_ERR_INVALID_ARGUMENT;
+  const int64_t total = static_cast<int64_t>(geom->rows) * geom->cols;
+  if (cell_begin < 0 || cell_end > total || cell_begin > cell_end) return AMB_ERR_SIZE_MISMATCH;
+  const double t0 = ambo::now();
+  Cloud cloud;
+  cloud.pts.resize(n);
+  for (size_t i = 0; i < n; ++i) { /* ortho-from-pcl.cc:29-34 */
+    cloud.pts[i].x = xyz[3 * i + 0];
+    cloud.pts[i].y = xyz[3 * i + 1];
+    cloud.pts[i].z = static_cast<double>(intensities[i]);
+  }
+  Adaptor adaptor(cloud);
+  KdTree tree(2, adaptor, nanoflann::KDTreeSingleIndexAdaptorParams(10)); /* :37-46 */
+  tree.buildIndex();
+  NanoflannSearcher searcher(tree);
+  const int st = ambo::runOrthoFromPclCellLoop(*geom, ortho, cloud.pts, searcher, interpolation_radius,
+                                               use_adaptive_interpolation != 0, num_threads, cell_begin, cell_end);
+  if (seconds) seconds[0] = ambo::now() - t0;
+  return st;
+}

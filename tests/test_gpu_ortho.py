@@ -257,3 +257,37 @@ def test_async_download_overlaps_but_returns_the_same_bits():
         outs.append({k: gm[k].copy() for k in ("elevation", "ortho", "elevation_angle", "observation_index")})
     for k in outs[0]:
         assert np.array_equal(outs[0][k].view(np.uint32), outs[1][k].view(np.uint32)), k
+
+
+def test_incremental_pipeline_like_the_demo_config_c5():
+    """main-ortho-backward-grid-incremental.cc:143-163 / BASELINE config C5 in miniature: one resident map, for
+    every batch Dsm::process on that batch's points (new tree, overwrite where non-empty) followed by
+    OrthoBackwardGrid::process on that batch's frames; state lives in the layers between calls."""
+    rows, cols, res = 160, 160, 0.5
+    camd, poses, imgs = make_inputs(rows, cols, res, 4, 5, 50.0, 0.08, False)   # 20 frames -> 4 batches of 5
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+    gm.to_device(0)
+    dsm = amb.Dsm(amb.DsmSettings(), gm)
+    ortho = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), gm)
+    g, cam = po.make_geometry(rows, cols, res), po.make_camera(**camd)
+    L = fresh_layers(rows, cols)
+    for b in range(4):
+        # the stereo pair of this batch sees one quarter of the map (a strip along y)
+        pts = synth.point_cloud(25000, rows * res / 2, cols * res / 8, seed=80 + b,
+                                center=(0.0, -cols * res / 2 + (b + 0.5) * cols * res / 4))
+        sl = slice(5 * b, 5 * b + 5)
+        dsm.process(pts, gm)
+        ortho.process(poses[sl], imgs[sl], gm)
+        assert po.dsm_process(g, L["elevation"], pts)[0] == 0
+        assert po.ortho_process(g, L, cam, poses[sl], imgs[sl])[0] == 0
+    gm.download()
+    assert ulp_diff(gm["elevation"], L["elevation"]).max() <= 1
+    assert np.array_equal(np.isnan(gm["elevation"]), np.isnan(L["elevation"]))
+    same_elev = gm["elevation"].view(np.uint32) == L["elevation"].view(np.uint32)
+    # where the two elevations agree bit for bit (all but a handful of last-ulp cells) the orthomosaic must too
+    oi_g, oi_o = gm["observation_index"], L["observation_index"]
+    mism = ~((oi_g == oi_o) | (np.isnan(oi_g) & np.isnan(oi_o))) & same_elev
+    assert mism.sum() == 0
+    assert (gm["ortho"][same_elev] == L["ortho"][same_elev]).all()
+    assert np.nanmax(oi_g) <= 4            # batch-relative indices
+    assert (~np.isnan(oi_g)).mean() > 0.5

@@ -24,6 +24,14 @@ def build_demo(tmp_path):
 def test_shim_headers_compile_and_link(tmp_path):
     amb.lib()
     assert os.path.exists(build_demo(tmp_path))
+    # the OrthoFromPcl drop-in has its own ortho::Settings: separate translation unit, like in the reference
+    src = tmp_path / "pcl.cc"
+    src.write_text("#include <aerial-mapper-ortho/ortho-from-pcl.h>\n"
+                   "int main() { ortho::Settings s; ortho::OrthoFromPcl o(s); (void)o; return 0; }\n")
+    libdir = os.path.join(ROOT, "aerial_mapper_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-DAMB_SHIM_MINI",
+                           "-I" + os.path.join(libdir, "shim"), str(src), "-o", str(tmp_path / "pcl"),
+                           "-L" + libdir, "-laerial_mapper_b200", "-Wl,-rpath," + libdir])
 
 
 @pytest.mark.gpu
