@@ -157,6 +157,15 @@ class GridMap(object):
             slab = self._slab(name)
             check(lib().amb_download_layer_async(ctx, LAYER_ID[name], slab.ctypes.data_as(C.c_void_p)), ctx)
 
+    def set_mirrors(self, names=HOT_LAYERS, enable=True):
+        """Register the host layers as mirrors (amb_set_host_mirror): process() streams every result layer back as
+        soon as it is final, overlapping later stages; sync() completes the copies.  Use pinned layers."""
+        ctx = self.context()
+        for name in names:
+            slab = self._slab(name)
+            ptr = slab.ctypes.data_as(C.c_void_p) if enable else None
+            check(lib().amb_set_host_mirror(ctx, LAYER_ID[name], ptr), ctx)
+
     def to_device(self, device=0, col_range=None, names=HOT_LAYERS):
         """Make the layers device-resident (uploads the current host values once)."""
         self._release()

@@ -21,6 +21,26 @@ int wait_layer_copy(amb_ctx* ctx, int layer) {
   return AMB_OK;
 }
 
+int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab) {
+  // ordered after everything enqueued so far on the compute stream, executed on the copy stream so that it
+  // overlaps later kernels and host->device copies (PCIe is full duplex)
+  AMB_CUDA(ctx, cudaEventRecord(ctx->copy_done[0], ctx->stream));
+  AMB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[0], 0));
+  AMB_CUDA(ctx, cudaMemcpyAsync(host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+  // later WRITERS of this layer on the compute stream wait for the copy (wait_layer_copy); readers do not
+  if (!ctx->layer_copy_event[layer])
+    AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->layer_copy_event[layer], cudaEventDisableTiming));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->layer_copy_event[layer], ctx->copy_stream));
+  ctx->layer_copy_pending[layer] = true;
+  return AMB_OK;
+}
+
+int mirror_layer(amb_ctx* ctx, int layer) {
+  if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer]) return AMB_OK;
+  return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
+}
+
 int ensure_layer(amb_ctx* ctx, int layer) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS) return AMB_ERR_INVALID_ARGUMENT;
   if (ctx->layers[layer]) return AMB_OK;
@@ -37,12 +57,22 @@ int ensure_layer(amb_ctx* ctx, int layer) {
   return AMB_OK;
 }
 
+// The flag travels through host-MAPPED memory (a store from a one-thread kernel), not through the device->host
+// copy engine, where it would queue behind result layers still streaming to their host mirrors.
+__global__ void flag_to_host_kernel(const unsigned int* __restrict__ src, unsigned int* __restrict__ dst) {
+  *dst = *src;
+  __threadfence_system();
+}
+
 static int finish_flags(amb_ctx* ctx, unsigned int offset_words, int err_code) {
-  unsigned int flag = 0;
-  AMB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->counters.as<unsigned int>() + offset_words, sizeof(flag),
-                                cudaMemcpyDeviceToHost, ctx->stream));
+  if (!ctx->host_flags)
+    AMB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->host_flags), 64, cudaHostAllocMapped));
+  unsigned int* mapped = nullptr;
+  AMB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&mapped), ctx->host_flags, 0));
+  ctx->host_flags[0] = 0;
+  flag_to_host_kernel<<<1, 1, 0, ctx->stream>>>(ctx->counters.as<unsigned int>() + offset_words, mapped);
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return flag ? err_code : AMB_OK;
+  return ctx->host_flags[0] ? err_code : AMB_OK;
 }
 
 }  // namespace amb
@@ -151,6 +181,10 @@ void amb_destroy(amb_ctx* ctx) {
     if (ctx->copy_done[k]) cudaEventDestroy(ctx->copy_done[k]);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layer_copy_event[l]) cudaEventDestroy(ctx->layer_copy_event[l]);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  ctx->stage.release();
+  if (ctx->stage_event) cudaEventDestroy(ctx->stage_event);
+  if (ctx->host_flags) cudaFreeHost(ctx->host_flags);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -220,17 +254,12 @@ int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab) {
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   int st = ensure_layer(ctx, layer);
   if (st != AMB_OK) return st;
-  // ordered after everything enqueued so far on the compute stream, executed on the copy stream so that it
-  // overlaps later kernels and host->device copies (PCIe is full duplex)
-  AMB_CUDA(ctx, cudaEventRecord(ctx->copy_done[0], ctx->stream));
-  AMB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[0], 0));
-  AMB_CUDA(ctx, cudaMemcpyAsync(host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float),
-                                cudaMemcpyDeviceToHost, ctx->copy_stream));
-  // later WRITERS of this layer on the compute stream wait for the copy (wait_layer_copy); readers do not
-  if (!ctx->layer_copy_event[layer])
-    AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->layer_copy_event[layer], cudaEventDisableTiming));
-  AMB_CUDA(ctx, cudaEventRecord(ctx->layer_copy_event[layer], ctx->copy_stream));
-  ctx->layer_copy_pending[layer] = true;
+  return enqueue_layer_download(ctx, layer, host_slab);
+}
+
+int amb_set_host_mirror(amb_ctx* ctx, int layer, float* host_slab) {
+  if (!ctx || layer < 0 || layer >= AMB_NUM_LAYERS) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->host_mirror[layer] = host_slab;
   return AMB_OK;
 }
 

@@ -42,6 +42,36 @@ struct DeviceBuffer {
   }
 };
 
+// Page-locked host staging for the small per-call tables (frame constants, cull data, bounding boxes ...).
+// Copies from PAGEABLE memory serialise with copies in flight on other streams; from pinned memory they do not,
+// which is what lets result downloads overlap the next stage.
+struct HostStage {
+  unsigned char* ptr = nullptr;
+  size_t bytes = 0, used = 0;
+  cudaError_t reserve(size_t want) {
+    if (want <= bytes) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    const size_t alloc = (want + 65535) & ~static_cast<size_t>(65535);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ptr), alloc, cudaHostAllocMapped);
+    if (e == cudaSuccess) bytes = alloc;
+    return e;
+  }
+  template <typename T>
+  T* take(size_t count) {  // 64-byte aligned slices; reserve() must have been called with the total
+    used = (used + 63) & ~static_cast<size_t>(63);
+    T* p = reinterpret_cast<T*>(ptr + used);
+    used += count * sizeof(T);
+    return p;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = used = 0;
+  }
+};
+
 enum EventId {
   EV_DSM_BEGIN = 0,
   EV_DSM_H2D_END,
@@ -66,6 +96,10 @@ struct amb_ctx {
   cudaStream_t copy_stream = nullptr;  // H2D staging overlapped with compute
   cudaEvent_t events[amb::EV_COUNT] = {};
   cudaEvent_t copy_done[2] = {};
+  amb::HostStage stage;                 // pinned staging of per-call tables
+  cudaEvent_t stage_event = nullptr;    // last use of `stage` by an asynchronous copy
+  unsigned int* host_flags = nullptr;   // pinned: device flags read back at the end of a host entry point
+  float* host_mirror[AMB_NUM_LAYERS] = {};  // pinned host slabs that receive a layer as soon as it is final
   cudaEvent_t layer_copy_event[AMB_NUM_LAYERS] = {};  // completion of an asynchronous download of that layer
   bool layer_copy_pending[AMB_NUM_LAYERS] = {};
   bool dsm_timed = false, ortho_timed = false, dsm_had_h2d = false, ortho_had_h2d = false;
@@ -121,6 +155,8 @@ inline int fail(amb_ctx* ctx, cudaError_t e, const char* what) {
 
 int ensure_layer(amb_ctx* ctx, int layer);
 int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for its pending asynchronous download
+int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab);  // on the copy stream, after current work
+int mirror_layer(amb_ctx* ctx, int layer);     // enqueue_layer_download to the registered host mirror, if any
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,

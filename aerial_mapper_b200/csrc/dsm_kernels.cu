@@ -1011,6 +1011,8 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   ctx->dsm_launches += 1;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
   AMB_CUDA(ctx, cudaGetLastError());
+  st = mirror_layer(ctx, out_layer);  // the result starts streaming to its host mirror (if one is registered)
+  if (st != AMB_OK) return st;
   ctx->dsm_debug_valid = ctx->dsm_debug;
   return AMB_OK;
 }

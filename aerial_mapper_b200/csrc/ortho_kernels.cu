@@ -383,6 +383,13 @@ __global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_co
   }
 }
 
+// Bounding boxes device -> HOST-MAPPED pinned memory with plain stores: the read-back must not queue behind the
+// result layers that are streaming to the host on the device->host copy engine.
+__global__ void copy_to_mapped_kernel(const int* __restrict__ src, int* __restrict__ dst, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[k] = src[k];
+  __threadfence_system();
+}
+
 // Phase B of the host-frame path: one thread per cell fetches the winner's texel from the uploaded sub-rectangle.
 struct FrameRect {
   const uint8_t* ptr;  // device copy of rows [y0, y1] x columns [x0, x1] of the frame
@@ -578,8 +585,14 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   const V3 t_C_B = {camera->t_C_B[0], camera->t_C_B[1], camera->t_C_B[2]};
   const V3 r_tmp = qrot(q_B_C, t_C_B);
   const V3 t_B_C = {-r_tmp.x, -r_tmp.y, -r_tmp.z};
-  std::vector<FrameConst> fcs(n);
-  std::vector<double> cull(12 * n);
+  // per-call tables live in pinned staging (see HostStage); the previous call's copies must have left it
+  if (!ctx->stage_event) AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_event, cudaEventDisableTiming));
+  AMB_CUDA(ctx, cudaEventSynchronize(ctx->stage_event));
+  AMB_CUDA(ctx, ctx->stage.reserve(n * (sizeof(FrameConst) + 12 * sizeof(double) + 8 * sizeof(int) +
+                                        sizeof(FrameRect) + sizeof(uint8_t*)) + 1024));
+  ctx->stage.used = 0;
+  FrameConst* fcs = ctx->stage.take<FrameConst>(n);
+  double* cull = ctx->stage.take<double>(12 * n);
   for (size_t f = 0; f < n; ++f) {
     const double* p = T_G_B + 7 * f;
     const Quat q_G_B = {p[3], p[4], p[5], p[6]};
@@ -605,10 +618,13 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   AMB_CUDA(ctx, ctx->counters.reserve(64));
   unsigned int* counters = ctx->counters.as<unsigned int>();
   AMB_CUDA(ctx, cudaMemsetAsync(counters + 8, 0, 4, s));
-  if (!select_only)
-    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, d_images, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
+  if (!select_only) {
+    const uint8_t** table = ctx->stage.take<const uint8_t*>(n);
+    for (size_t f = 0; f < n; ++f) table[f] = d_images[f];
+    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, table, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
+  }
   AMB_CUDA(ctx, ctx->frame_cull.reserve(12 * n * sizeof(double)));
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull.data(), 12 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull, 12 * n * sizeof(double), cudaMemcpyHostToDevice, s));
 
   OrthoArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -617,16 +633,20 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   a.observation_index = ctx->layers[AMB_LAYER_OBSERVATION_INDEX];
   a.out_layer = ctx->layers[out_layer];
   a.error_flag = counters + 8;
-  std::vector<int> bbox;
+  int* bbox = nullptr;      // pinned: initial values up, results back
+  int* bbox_back = nullptr;
   const size_t cells = ctx->slab_cells();
   if (select_only) {
     AMB_CUDA(ctx, ctx->ortho_pix.reserve(cells * sizeof(unsigned int)));
     AMB_CUDA(ctx, ctx->ortho_bbox.reserve(n * 4 * sizeof(int)));
     AMB_CUDA(ctx, cudaMemsetAsync(ctx->ortho_pix.ptr, 0xff, cells * sizeof(unsigned int), s));
-    bbox.assign(4 * n, -1);
-    for (size_t f = 0; f < n; ++f) bbox[4 * f + 0] = bbox[4 * f + 1] = 0x7fffffff;
-    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->ortho_bbox.ptr, bbox.data(), bbox.size() * sizeof(int),
-                                  cudaMemcpyHostToDevice, s));
+    bbox = ctx->stage.take<int>(4 * n);
+    bbox_back = ctx->stage.take<int>(4 * n);
+    for (size_t f = 0; f < n; ++f) {
+      bbox[4 * f + 0] = bbox[4 * f + 1] = 0x7fffffff;
+      bbox[4 * f + 2] = bbox[4 * f + 3] = -1;
+    }
+    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->ortho_bbox.ptr, bbox, 4 * n * sizeof(int), cudaMemcpyHostToDevice, s));
     a.pix = ctx->ortho_pix.as<unsigned int>();
     a.bbox = ctx->ortho_bbox.as<int>();
   }
@@ -662,8 +682,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   ctx->ortho_launches = 0;
   for (size_t f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {  // ascending chunks keep the frame order
     const size_t nf = std::min<size_t>(kMaxFramesPerLaunch, n - f0);
-    // The staging vector must outlive the async copy; pageable source -> the copy is staged before returning.
-    AMB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_frames, fcs.data() + f0, nf * sizeof(FrameConst), 0,
+    AMB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_frames, fcs + f0, nf * sizeof(FrameConst), 0,
                                           cudaMemcpyHostToDevice, s));
     a.n_frames = static_cast<int>(nf);
     a.frame_base = static_cast<int>(f0);
@@ -689,13 +708,25 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   }
   AMB_CUDA(ctx, cudaGetLastError());
   ctx->ortho_h2d_bytes = 0;
-  if (!select_only) return AMB_OK;
+  // elevation_angle and observation_index are final here: start streaming them to their host mirrors
+  int mst = mirror_layer(ctx, AMB_LAYER_ELEVATION_ANGLE);
+  if (mst == AMB_OK) mst = mirror_layer(ctx, AMB_LAYER_OBSERVATION_INDEX);
+  if (mst != AMB_OK) return mst;
+  if (!select_only) {
+    AMB_CUDA(ctx, cudaEventRecord(ctx->stage_event, s));
+    return mirror_layer(ctx, out_layer);
+  }
 
   // ---- host frames: bounding boxes back, sub-rectangles up, texel gather ----
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_SELECT_END], s));
-  AMB_CUDA(ctx, cudaMemcpyAsync(bbox.data(), ctx->ortho_bbox.ptr, bbox.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  {
+    int* mapped = nullptr;
+    AMB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&mapped), bbox_back, 0));
+    copy_to_mapped_kernel<<<8, 256, 0, s>>>(ctx->ortho_bbox.as<int>(), mapped, static_cast<int>(4 * n));
+  }
   AMB_CUDA(ctx, cudaStreamSynchronize(s));
-  std::vector<FrameRect> rects(n);
+  bbox = bbox_back;
+  FrameRect* rects = ctx->stage.take<FrameRect>(n);
   size_t total = 0;
   for (size_t f = 0; f < n; ++f) {
     FrameRect& r = rects[f];
@@ -725,14 +756,14 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     off += static_cast<size_t>(r.pitch) * h;
     r.pad_ = 0;
   }
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_rects.ptr, rects.data(), n * sizeof(FrameRect), cudaMemcpyHostToDevice, s));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_rects.ptr, rects, n * sizeof(FrameRect), cudaMemcpyHostToDevice, s));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_COPY_END], s));
   ortho_texel_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(a.pix, a.observation_index, ctx->frame_rects.as<FrameRect>(),
                                                     a.out_layer, cells, channels, a.colored);
   ctx->ortho_launches += 1;
   AMB_CUDA(ctx, cudaGetLastError());
-  // `rects` is pageable: the async copy above was staged before returning
-  return AMB_OK;
+  AMB_CUDA(ctx, cudaEventRecord(ctx->stage_event, s));
+  return mirror_layer(ctx, out_layer);
 }
 
 }  // namespace amb

@@ -289,6 +289,7 @@ def run_ours(args):
         gmh = gm_h.getMutable()
         gmh.to_device(local_rank, col_range=(c0, c1), names=layer_names)  # layers live in HBM between calls
         ctx_h = gmh.context()
+        gmh.set_mirrors(layer_names)   # result layers stream back to the (pinned) host map as they become final
         if world > 1:
             amb.check(amb.lib().amb_dsm_set_density_hint(ctx_h, n_points / float(rows * cols)), ctx_h)
         dsm_h = amb.Dsm(amb.DsmSettings(), gmh)
@@ -305,10 +306,8 @@ def run_ours(args):
                 dsm_h.process_device(hx.big_xyz.data_ptr(), hx.n_total, gmh, d_ids=hx.big_ids.data_ptr())
             else:
                 dsm_h.process(xyz_np, gmh)        # amb_dsm_process: HOST points -> H2D inside
-            gmh.download_async(("elevation",))    # DSM result starts streaming back while the ortho stage runs
             ortho_h.process(poses, img_np, gmh)   # amb_ortho_process: HOST frames -> needed sub-rectangles H2D
-            gmh.download(("ortho", "elevation_angle", "observation_index"))
-            gmh.sync()                            # all four result layers are in host memory
+            gmh.sync()                            # amb_sync: all four result layers are in host memory
 
         e2e_steps = max(1, min(args.steps, 3))
         step_e2e()
@@ -328,7 +327,7 @@ def run_ours(args):
                "frames_host_bytes": int(n_frames * H * W),
                "api": "C ABI through the Python mirror, HOST inputs/outputs (pinned): amb_init_layers, "
                       "amb_dsm_process(host xyz), amb_ortho_process(host frames; only the winners' "
-                      "sub-rectangles cross PCIe), amb_download_layer(_async) x4, amb_sync"}
+                      "sub-rectangles cross PCIe), result layers through amb_set_host_mirror (x4), amb_sync"}
         del gm_h, gmh
 
     if rank != 0:

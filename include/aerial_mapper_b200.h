@@ -144,6 +144,12 @@ int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab);
 /* Same, asynchronous: the copy is ordered after the work enqueued so far and runs on a second stream, so it
  * overlaps later kernels and host->device copies (use page-locked host memory); amb_sync() completes it. */
 int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab);
+/* Register (or clear with NULL) a page-locked host slab as the MIRROR of a layer: every process() call then starts
+ * copying that layer to it as soon as the layer is final (elevation right after the DSM kernels; elevation_angle
+ * and observation_index right after the winners are selected, while the frame rectangles are still being
+ * uploaded; the ortho layer after the texel gather), on a second stream.  amb_sync() completes the copies.  This is
+ * the host-authoritative model of the reference (process() mutates the caller's map) without serialising PCIe. */
+int amb_set_host_mirror(amb_ctx* ctx, int layer, float* host_slab);
 /* Device pointer of a layer slab (allocating it if needed), for device-side consumers (NCCL all-gather of
  * finished stripes, downstream kernels). */
 int amb_layer_device_ptr(amb_ctx* ctx, int layer, float** device_slab);

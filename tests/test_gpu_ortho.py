@@ -291,3 +291,23 @@ def test_incremental_pipeline_like_the_demo_config_c5():
     assert (gm["ortho"][same_elev] == L["ortho"][same_elev]).all()
     assert np.nanmax(oi_g) <= 4            # batch-relative indices
     assert (~np.isnan(oi_g)).mean() > 0.5
+
+
+def test_host_mirrors_stream_results_back_with_the_same_bits():
+    rows, cols, res = 128, 96, 0.5
+    xyz = synth.point_cloud(30000, 33.0, 25.0, seed=44)
+    camd, poses, imgs = make_inputs(rows, cols, res, 2, 3, 50.0, 0.08, False)
+    ref = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+    amb.Dsm(amb.DsmSettings(), ref).process(xyz, ref)
+    amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), ref).process(poses, imgs, ref)
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res), pinned=True).getMutable()
+    gm.to_device(0)
+    names = ("ortho", "elevation", "elevation_angle", "observation_index")
+    gm.set_mirrors(names)
+    for _ in range(2):   # second round: init + writers must wait for the previous round's mirror copies
+        amb.check(amb.lib().amb_init_layers(gm.context()), gm.context())
+        amb.Dsm(amb.DsmSettings(), gm).process(xyz, gm)
+        amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), gm).process(poses, imgs, gm)
+        gm.sync()
+        for k in names:
+            assert np.array_equal(gm[k].view(np.uint32), ref[k].view(np.uint32)), k
