@@ -96,29 +96,47 @@ class HaloExchange(object):
         self.local_ids = self.big_ids[world * self.cap:]
         self.n_total = world * self.cap + n
 
+    def use_stream(self, stream):
+        """Run the torch-side plumbing (fills, copies, the NCCL call) on `stream` — pass
+        torch.cuda.ExternalStream(amb_stream(ctx)) so that everything is ordered on the library's own stream and no
+        host synchronisation is needed between the compaction kernel, the all-gather and the DSM kernels."""
+        self.stream = stream
+
+    def _on_stream(self):
+        import contextlib
+        st = getattr(self, "stream", None)
+        return self.torch.cuda.stream(st) if st is not None else contextlib.nullcontext()
+
     def extract(self, ctx, y_lo, y_hi, reach, center_easting=0.0):
         """Fill the send buffer with this rank's border points (hand-written compaction kernel, ctx's stream)."""
         import ctypes as C
         from ._lib import check, lib
-        self.send.fill_(float("nan"))
-        self.torch.cuda.current_stream().synchronize()
+        shared = getattr(self, "stream", None) is not None
+        with self._on_stream():
+            self.send.fill_(float("nan"))
+        if not shared:
+            self.torch.cuda.current_stream().synchronize()
         base = self.send.data_ptr()
         check(lib().amb_dsm_extract_halo(ctx, C.c_void_p(self.local_xyz.data_ptr()),
                                          C.c_void_p(self.local_ids.data_ptr()), self.n_local, float(y_lo),
                                          float(y_hi), float(reach), float(center_easting), C.c_void_p(base),
                                          C.c_void_p(base + 8 * 3 * self.cap), self.cap,
                                          C.c_void_p(base + 8 * 4 * self.cap)), ctx)
-        check(lib().amb_sync(ctx), ctx)
+        if not shared:
+            check(lib().amb_sync(ctx), ctx)
 
     def exchange(self, dist):
-        dist.all_gather_into_tensor(self.gathered.view(-1), self.send)  # the one collective of the DSM stage
+        with self._on_stream():
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.send)  # the one collective of the DSM stage
 
     def assemble(self):
         cap, w = self.cap, self.world
-        self.big_xyz[:w * cap] = self.gathered[:, :3 * cap].reshape(w * cap, 3)
-        self.big_ids[:w * cap] = self.gathered[:, 3 * cap:4 * cap].reshape(-1).view(self.torch.int64)
-        self.big_xyz[self.rank * cap:(self.rank + 1) * cap] = float("nan")  # own halo: already among the local points
-        self.torch.cuda.current_stream().synchronize()
+        with self._on_stream():
+            self.big_xyz[:w * cap] = self.gathered[:, :3 * cap].reshape(w * cap, 3)
+            self.big_ids[:w * cap] = self.gathered[:, 3 * cap:4 * cap].reshape(-1).view(self.torch.int64)
+            self.big_xyz[self.rank * cap:(self.rank + 1) * cap] = float("nan")  # own halo: already local
+        if getattr(self, "stream", None) is None:
+            self.torch.cuda.current_stream().synchronize()
 
     def counts(self):
         """Halo sizes reported by every rank (host read; > cap means a truncated halo)."""

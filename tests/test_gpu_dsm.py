@@ -235,7 +235,8 @@ def test_property_neighbour_checksum_large():
     assert int(cnt.astype(np.int64).sum()) == total
 
 
-def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map():
+@pytest.mark.parametrize("on_library_stream", [False, True])
+def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map(on_library_stream):
     """every rank holds only the points of its own stripe; the border halos are compacted by
     amb_dsm_extract_halo and exchanged (here: three ranks simulated one after the other on one GPU)."""
     import torch
@@ -255,15 +256,22 @@ def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map()
         y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
         m = sharding.owner_mask(xyz[:, 1], y_lo, y_hi, r, world)
         hx = sharding.HaloExchange(torch, world, r, 20000, xyz[m], ids[m], dev)
+        if on_library_stream:  # torch plumbing ordered on the context's own stream, no host syncs
+            hx.use_stream(torch.cuda.ExternalStream(amb.lib().amb_stream(gm.context()), device=dev))
         reach = amb.lib().amb_dsm_halo_reach(ctypes_byref(gm.geometry), 1)
         amb.check(amb.lib().amb_dsm_set_density_hint(gm.context(), xyz.shape[0] / float(rows * cols)), gm.context())
         hx.extract(gm.context(), y_lo, y_hi, reach)
         gms.append((gm, c0, c1))
         exch.append(hx)
     assert sum(h.n_local for h in exch) == xyz.shape[0]          # the stripes partition the cloud
+    torch.cuda.synchronize()
+    for gm, _, _ in gms:
+        gm.sync()
     gathered = torch.stack([h.send for h in exch])               # what the all-gather would deliver
+    torch.cuda.synchronize()
     for r, (hx, (gm, c0, c1)) in enumerate(zip(exch, gms)):
         hx.gathered.copy_(gathered)
+        torch.cuda.synchronize()
         assert (hx.counts() <= hx.cap).all() and (hx.counts() > 0).all()
         hx.assemble()
         d = amb.Dsm(amb.DsmSettings(), gm)
