@@ -218,8 +218,8 @@ def run_ours(args):
         cap = int(n_points * (2.0 * reach) / (2.0 * half_y) * 1.5) + 4096
         hx = sharding.HaloExchange(torch, world, rank, cap, xyz_d[own], ids_all[own], device)
         amb.check(amb.lib().amb_dsm_set_density_hint(ctx, n_points / float(rows * cols)), ctx)
-        if os.environ.get("AMB_BENCH_HOST_SYNC_HALO") != "1":
-            # torch plumbing + NCCL on the library's own stream: no host sync inside the halo step
+        if os.environ.get("AMB_BENCH_STREAM_HALO") == "1":
+            # opt-in: torch plumbing + NCCL on the library's own stream, no host sync inside the halo step
             hx.use_stream(torch.cuda.ExternalStream(amb.lib().amb_stream(ctx), device=device))
         del xyz_d, ids_all, own
         torch.cuda.empty_cache()
@@ -303,7 +303,7 @@ def run_ours(args):
             amb.check(amb.lib().amb_init_layers(ctx_h), ctx_h)  # AerialGridMap::initialize values, device side
             if world > 1:
                 hx.use_stream(torch.cuda.ExternalStream(amb.lib().amb_stream(ctx_h), device=device)
-                              if os.environ.get("AMB_BENCH_HOST_SYNC_HALO") != "1" else None)
+                              if os.environ.get("AMB_BENCH_STREAM_HALO") == "1" else None)
                 with hx._on_stream():
                     hx.local_xyz.copy_(xyz_h, non_blocking=True)   # this rank's share of the cloud: host -> device
                 hx.extract(ctx_h, y_lo, y_hi, reach)
