@@ -15,6 +15,7 @@
 // a block read the same frame at the same time, i.e. a constant-cache broadcast.
 #include <cfloat>
 #include <cmath>
+#include <mutex>
 
 #include "amb_context.h"
 
@@ -34,6 +35,15 @@ struct FrameConst {
 static_assert(sizeof(FrameConst) * kMaxFramesPerLaunch <= 64 * 1024, "constant memory budget");
 
 __constant__ FrameConst c_frames[kMaxFramesPerLaunch];
+
+// c_frames is one symbol per device: launches of different contexts (streams) on the same device must not
+// overwrite it while another context's kernel still reads it.  Every upload waits for the previous user's kernel
+// (an event per device), whatever stream that was on.
+struct ConstantGuard {
+  std::mutex mu;
+  cudaEvent_t last_use[64] = {};
+};
+ConstantGuard g_constant_guard;
 
 struct OrthoArgs {
   const float* elevation;
@@ -682,6 +692,10 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   ctx->ortho_launches = 0;
   for (size_t f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {  // ascending chunks keep the frame order
     const size_t nf = std::min<size_t>(kMaxFramesPerLaunch, n - f0);
+    std::lock_guard<std::mutex> lock(g_constant_guard.mu);  // held until this chunk's kernel has been enqueued
+    cudaEvent_t& guard_event = g_constant_guard.last_use[ctx->device & 63];
+    if (!guard_event) AMB_CUDA(ctx, cudaEventCreateWithFlags(&guard_event, cudaEventDisableTiming));
+    AMB_CUDA(ctx, cudaStreamWaitEvent(s, guard_event, 0));
     AMB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_frames, fcs + f0, nf * sizeof(FrameConst), 0,
                                           cudaMemcpyHostToDevice, s));
     a.n_frames = static_cast<int>(nf);
@@ -705,6 +719,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
       ortho_kernel<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
     }
     ctx->ortho_launches += 1;
+    AMB_CUDA(ctx, cudaEventRecord(guard_event, s));
   }
   AMB_CUDA(ctx, cudaGetLastError());
   ctx->ortho_h2d_bytes = 0;
