@@ -14,7 +14,6 @@ All compute happens in libaerial_mapper_b200.so on the GPU; there is no CPU path
 """
 import ctypes as C
 import logging
-import math
 
 import numpy as np
 

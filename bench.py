@@ -50,7 +50,6 @@ WORKLOADS = {
 
 DSM_BYTES_PER_POINT = 24  # read each point once
 DSM_BYTES_PER_CELL = 4    # write each elevation once
-ORTHO_BYTES_PER_CELL_GRAY = 21
 
 
 def parse_args():
@@ -139,17 +138,6 @@ def device_point_cloud(torch, n, half_x, half_y, device, seed=2):
     xyz[:, 2] = (100.0 + 10.0 * torch.sin(0.01 * xyz[:, 0]) * torch.cos(0.01 * xyz[:, 1]) +
                  0.05 * torch.randn(n, generator=g, device=device, dtype=torch.float64))
     return xyz
-
-
-def cuda_array(torch, ptr, shape_f32, device):
-    """Wrap a device pointer owned by the C library as a torch float32 tensor (NCCL plumbing)."""
-    class _W(object):
-        pass
-    w = _W()
-    n = int(np.prod(shape_f32))
-    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
-                                  "strides": None}
-    return torch.as_tensor(w, device=device)
 
 
 def run_ours(args):
