@@ -6,8 +6,9 @@ The compute lives in libaerial_mapper_b200.so (hand-written sm_100a CUDA, C ABI 
 from ._lib import (AMB_OK, AmbError, Camera, Geometry, LAYER_ID, LAYER_NAMES, DIST_EQUIDISTANT, DIST_NONE,
                    DIST_RADTAN, LIB_PATH, build, check, lib)
 from .api import (AerialGridMap, Dsm, DsmSettings, GridMap, GridMapSettings, HOT_LAYERS, NCamera,
-                  OrthoBackwardGrid, OrthoFromPcl, OrthoFromPclSettings, OrthoSettings, dsm_thresholds)
+                  OrthoBackwardGrid, OrthoFromPcl, OrthoFromPclSettings, OrthoSettings, compute_point_cloud,
+                  dsm_thresholds)
 
 __all__ = ["AMB_OK", "AmbError", "Camera", "Geometry", "LAYER_ID", "LAYER_NAMES", "DIST_EQUIDISTANT", "DIST_NONE",
            "DIST_RADTAN", "LIB_PATH", "build", "check", "lib", "AerialGridMap", "Dsm", "DsmSettings", "GridMap",
-           "GridMapSettings", "HOT_LAYERS", "NCamera", "OrthoBackwardGrid", "OrthoFromPcl", "OrthoFromPclSettings", "OrthoSettings", "dsm_thresholds"]
+           "GridMapSettings", "HOT_LAYERS", "NCamera", "OrthoBackwardGrid", "OrthoFromPcl", "OrthoFromPclSettings", "OrthoSettings", "compute_point_cloud", "dsm_thresholds"]

@@ -441,3 +441,32 @@ class OrthoFromPcl(object):
                                                1 if s.use_adaptive_interpolation else 0), ctx)
         if not map.is_resident():
             map.download(("ortho",))
+
+
+K_MAX_INVALID_DISPARITY = 1  # stereo::Densifier::kMaxInvalidDisparity (densifier.h:49)
+
+
+def compute_point_cloud(disparity_map, image_left, K, baseline, R_G_C, t_G_C1, device=0,
+                        max_invalid_disparity=K_MAX_INVALID_DISPARITY):
+    """stereo::Densifier::computePointCloud (densifier.cpp:25-108; "next" row N3): disparity map (float32 [H, W]) +
+    left rectified image (uint8 [H, W]) -> (point_cloud_eigen float64 [n, 3], point_cloud_intensities int32 [n]) in
+    raster order.  K is the 3x3 camera matrix of the rectified pair (or (fx, fy, cx, cy))."""
+    disp = np.ascontiguousarray(disparity_map, dtype=np.float32)
+    img = np.ascontiguousarray(image_left, dtype=np.uint8)
+    h, w = disp.shape
+    if img.shape != (h, w):
+        raise AmbError(_lib.AMB_ERR_SIZE_MISMATCH, "CHECK_EQ(image_resolution_, disparity_map.size())")
+    K = np.asarray(K, dtype=np.float64)
+    k4 = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]]) if K.shape == (3, 3) else K.reshape(4).copy()
+    R = np.ascontiguousarray(R_G_C, dtype=np.float64).reshape(9)
+    t = np.ascontiguousarray(t_G_C1, dtype=np.float64).reshape(3)
+    cap = h * w
+    xyz = np.empty((cap, 3), dtype=np.float64)
+    inten = np.empty(cap, dtype=np.int32)
+    n = C.c_size_t(0)
+    check(lib().amb_stereo_reproject(int(device), disp.ctypes.data_as(C.c_void_p), w, img.ctypes.data_as(C.c_void_p),
+                                     w, w, h, k4.ctypes.data_as(C.c_void_p), float(baseline),
+                                     R.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
+                                     float(max_invalid_disparity), xyz.ctypes.data_as(C.c_void_p),
+                                     inten.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+    return xyz[:n.value].copy(), inten[:n.value].copy()

@@ -206,6 +206,26 @@ int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* i
 int amb_ortho_from_pcl_process_device(amb_ctx* ctx, const double* d_xyz, const int32_t* d_intensities, size_t n,
                                       int32_t interpolation_radius, int32_t use_adaptive_interpolation);
 
+/* ---- "next" row N3: stereo::Densifier::computePointCloud (aerial_mapper_dense_pcl/src/densifier.cpp:25-108) ----
+ * Disparity map -> world points, the step right before Dsm::process in the incremental pipeline
+ * (stereo.cpp:149-193).  For every pixel in raster order with disparity > max_invalid_disparity
+ * (Densifier::kMaxInvalidDisparity = 1): w = d / baseline; p = ((u-cx)/w, (fx/fy*v - cy*fx/fy)/w, fx/w);
+ * P = R_G_C p + t_G_C1; kept unless (float)P.z is infinite.  Kept points (double[3]) and their gray values are
+ * written in raster order (point_cloud_eigen / point_cloud_intensities).  K = {fx, fy, cx, cy}; R_G_C row-major.
+ * *out_count = number of valid points (may exceed capacity: only the first `capacity` were written).
+ * Strides are in elements (floats / bytes) per row. */
+int amb_stereo_reproject(int device, const float* disparity, size_t disparity_stride, const uint8_t* image_left,
+                         size_t image_stride, int32_t width, int32_t height, const double* K, double baseline,
+                         const double* R_G_C, const double* t_G_C1, float max_invalid_disparity, double* out_xyz,
+                         int32_t* out_intensity, size_t capacity, size_t* out_count);
+/* Same with device buffers on `stream` (a cudaStream_t as void*, may be NULL); d_block_scratch needs
+ * ceil(width*height/256) uint32; d_count receives the number of valid points.  Asynchronous. */
+int amb_stereo_reproject_device(int device, void* stream, const float* d_disparity, size_t disparity_stride,
+                                const uint8_t* d_image_left, size_t image_stride, int32_t width, int32_t height,
+                                const double* K, double baseline, const double* R_G_C, const double* t_G_C1,
+                                float max_invalid_disparity, double* d_out_xyz, int32_t* d_out_intensity,
+                                size_t capacity, uint32_t* d_block_scratch, unsigned long long* d_count);
+
 /* ---- Orthomosaic: ortho::OrthoBackwardGrid::process (ortho-backward-grid.cc:223-239) ---- */
 /* T_G_B: n poses, 7 doubles each in the order of the reference's pose files: x y z qw qx qy qz
  * (aerial-mapper-io.cc:110).  images: n host pointers to H x W x channels uint8 rasters with `row_step` bytes

@@ -34,7 +34,8 @@ class Camera(C.Structure):
 def build(force=False):
     """Compile liboracle.so (always possible) and oracle/_ref (only where /root/reference exists)."""
     need = force or not os.path.exists(_LIB_PATH)
-    srcs = ["dsm_oracle.cc", "ortho_oracle.cc", "dsm_cell_loop.h", "oracle_common.h", "amb_oracle.h"]
+    srcs = ["dsm_oracle.cc", "ortho_oracle.cc", "stereo_oracle.cc", "dsm_cell_loop.h", "oracle_common.h",
+            "amb_oracle.h"]
     if not need:
         t = os.path.getmtime(_LIB_PATH)
         need = any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in srcs)
@@ -76,6 +77,10 @@ def lib():
         L.ambo_ortho_process.restype = C.c_int
         L.ambo_ortho_from_pcl_process.argtypes = _PCL_ARGS
         L.ambo_ortho_from_pcl_process.restype = C.c_int
+        L.ambo_stereo_reproject.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ambo_stereo_reproject.restype = C.c_int
         L.ambo_project3.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p]
         L.ambo_project3.restype = C.c_int
         L.ambo_transform_to_camera.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]
@@ -165,6 +170,22 @@ def ortho_from_pcl_process(geom, ortho, xyz, intensities, radius=2, adaptive=Fal
     fn = ref().ambo_ref_ortho_from_pcl_process if use_ref else lib().ambo_ortho_from_pcl_process
     return fn(C.byref(geom), _ptr(ortho), _ptr(xyz), _ptr(inten), n, int(radius), 1 if adaptive else 0,
               int(num_threads), lo, hi, None)
+
+
+def stereo_reproject(disparity, image_left, k4, baseline, R_G_C, t_G_C1, max_invalid_disparity=1.0):
+    """Oracle Densifier::computePointCloud.  Returns (status, xyz [n,3] float64, intensities [n] int32)."""
+    disp = np.ascontiguousarray(disparity, dtype=np.float32)
+    img = np.ascontiguousarray(image_left, dtype=np.uint8)
+    h, w = disp.shape
+    k4 = np.ascontiguousarray(k4, dtype=np.float64)
+    R = np.ascontiguousarray(R_G_C, dtype=np.float64).reshape(9)
+    t = np.ascontiguousarray(t_G_C1, dtype=np.float64).reshape(3)
+    xyz = np.empty((h * w, 3), np.float64)
+    inten = np.empty(h * w, np.int32)
+    n = C.c_size_t(0)
+    st = lib().ambo_stereo_reproject(_ptr(disp), w, _ptr(img), w, w, h, _ptr(k4), float(baseline), _ptr(R), _ptr(t),
+                                     float(max_invalid_disparity), _ptr(xyz), _ptr(inten), h * w, C.byref(n))
+    return st, xyz[:n.value].copy(), inten[:n.value].copy()
 
 
 def ortho_process(geom, layers, camera, T_G_B, images, colored=False, num_threads=0, cell_range=None):
