@@ -285,3 +285,58 @@ def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map(o
 def ctypes_byref(x):
     import ctypes
     return ctypes.byref(x)
+
+
+def test_property_full_baseline_size_c2():
+    """BASELINE config C2 at full size (50 M points -> 10000 x 10000 @ 0.25 m) through size-independent
+    properties: IDW of a constant is that constant in every cell, no cell is left empty at 8 points / m^2, the
+    neighbour-count checksum over a 64-column band equals an independent torch evaluation."""
+    import torch
+    rows = cols = 10000
+    res, n = 0.25, 50_000_000
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    xyz = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    xyz[:, 0] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * 1250
+    xyz[:, 1] = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * 1250
+    xyz[:, 2] = 77.5
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res),
+                           layer_names=("elevation",)).getMutable()
+    gm.to_device(0, names=("elevation",))
+    d = amb.Dsm(amb.DsmSettings(), gm)
+    d.process_device(xyz.data_ptr(), n, gm)
+    gm.sync()
+    t = gm.timings()
+    assert t["dsm_points_binned"] == n and t["dsm_cells_empty"] == 0
+    gm.download(("elevation",))
+    e = gm["elevation"]
+    assert not np.isnan(e).any() and (e == np.float32(77.5)).all()
+    del gm
+    # checksum on a band of columns (stripe context + debug counters keep the footprint small)
+    band = (4992, 5056)
+    gb = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res),
+                           layer_names=("elevation",)).getMutable()
+    gb.to_device(0, col_range=band, names=("elevation",))
+    db = amb.Dsm(amb.DsmSettings(), gb)
+    db.debug = True
+    db.process_device(xyz.data_ptr(), n, gb)
+    gb.sync()
+    db._fetch_debug(gb)
+    cnt, lvl = db.last_debug
+    assert (lvl == 0).all()
+    base = 0.5 * rows * res - 0.5 * res
+    py = xyz[:, 1]
+    near = (py < base - res * band[0] + 1.2) & (py > base - res * (band[1] - 1) - 1.2)
+    px, py = xyz[near, 0], py[near]
+    ci = torch.floor((base - px) / res + 0.5).to(torch.int64)
+    cj = torch.floor((base - py) / res + 0.5).to(torch.int64)
+    total = 0
+    for di in range(-5, 6):
+        for dj in range(-5, 6):
+            i, j = ci + di, cj + dj
+            inside = (i >= 0) & (i < rows) & (j >= band[0]) & (j < band[1])
+            qx = base + res * (-(i.to(torch.float64)))
+            qy = base + res * (-(j.to(torch.float64)))
+            dx, dy = qx - px, qy - py
+            total += int((((dx * dx + dy * dy) < 1.0) & inside).sum().item())
+    assert int(cnt.astype(np.int64).sum()) == total
