@@ -4,18 +4,22 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
  * The product library (aerial_mapper_b200/csrc) never links, loads or calls anything under oracle/.
  *
- * PARITY UNPINNED: the reference (ethz-asl/aerial_mapper @ /root/reference) ships no tests, golden vectors or
- * fixtures for this path, and its own translation units (dsm.cc, ortho-backward-grid.cc)
- * cannot be compiled here (they need ROS, catkin, grid_map, aslam_cv2, minkindr, Eigen, OpenCV, glog — all
- * absent, no network).  What pins this oracle instead:
- *   - oracle/_ref/libamb_oracle_ref.so compiles the reference's vendored nanoflann.hpp VERBATIM from
- *     /root/reference (the DSM's whole neighbour search) around the restated cell loop; the dependency-free
- *     restatement in dsm_oracle.cc is checked against it (tests/test_oracle_dsm.py);
- *   - brute force / scipy.spatial.cKDTree for neighbour sets, cv2.projectPoints for the camera model,
- *     scipy Rotation for the pose algebra (tests/test_oracle_*.py);
- *   - golden fixtures under tests/golden/ generated by this oracle (tests/golden/make_golden.py).
- * The grid_map / aslam_cv2 / minkindr arithmetic is restated from upstream knowledge of those (un-versioned,
- * install/dependencies_https.rosinstall:1,9,11) dependencies; see each function's comment.
+ * PINNING.  The reference (ethz-asl/aerial_mapper @ /root/reference) ships no tests, golden vectors or fixtures for
+ * this path and its packages cannot be built as they are (ROS, catkin, grid_map, aslam_cv2,
+ * minkindr, Eigen, OpenCV, glog — all absent, no network).  What pins this oracle:
+ *   - oracle/_ref/libamb_refsrc_{main,pcl}.so: the reference's OWN dsm.cc, ortho-backward-grid.cc, ortho-from-pcl.cc,
+ *     utils-common.cc and the reference headers they include (nanoflann.hpp among them) compiled VERBATIM from where
+ *     they lie, against stand-in headers for the absent third-party libraries (refsrc_stubs/amb_refsrc_deps.h lists
+ *     exactly what is reference code and what is restated).  tests/test_oracle_refsrc.py: the restated loops are
+ *     bit-identical to the reference's own code on every layer; the committed golden fixtures likewise.
+ *   - oracle/_ref/libamb_oracle_ref.so: nanoflann.hpp verbatim around the restated cell loop (exposes neighbour
+ *     counts / retry levels); the dependency-free restatement in dsm_oracle.cc is checked against it.
+ *   - brute force / scipy.spatial.cKDTree for neighbour sets, cv2.projectPoints for the camera model, scipy Rotation
+ *     for the pose algebra (tests/test_oracle_*.py).
+ * PARITY UNPINNED for one part only: the arithmetic of the un-vendored, un-versioned dependencies
+ * (install/dependencies_https.rosinstall:1,9,11) — grid_map's cell-centre formula and colour packing, aslam_cv2's
+ * pinhole/distortion projection, minkindr's pose algebra — is restated from their upstream sources
+ * (thirdparty_math.h, oracle_common.h) in both the stand-ins and the restatement.
  */
 #ifndef AMB_ORACLE_H_
 #define AMB_ORACLE_H_

@@ -4,164 +4,18 @@
  * Reference: aerial_mapper_ortho/src/ortho-backward-grid.cc:223-239 (process: pose composition + dispatch),
  * :128-221 (multi-thread cell loop; the single-thread twin :42-126 has the same arithmetic).
  *
- * External arithmetic (sources NOT under /root/reference; restated from upstream knowledge, un-versioned deps
- * install/dependencies_https.rosinstall:1,11):
- *   minkindr  QuatTransformation: operator*, inverse(), transform()  -> struct Transformation below
- *   Eigen     Quaternion product and Quaternion::_transformVector     -> quatMul / quatRotate
- *   aslam_cv2 PinholeCamera::project3 + RadTan / Equidistant distortion -> project3()
- *   grid_map  colorVectorToValue                                       -> ambo_pack_color
- * Cross-checked in tests/test_oracle_ortho.py against cv2.projectPoints, cv2.fisheye.projectPoints and
- * scipy.spatial.transform.Rotation.
+ * External arithmetic (minkindr, Eigen quaternions, aslam_cv2 pinhole + distortion, grid_map colour packing — sources
+ * NOT under /root/reference) lives in thirdparty_math.h, shared with the stand-in headers oracle/_ref's build of the
+ * reference's own ortho-backward-grid.cc is compiled against (refsrc_stubs/).
  */
 #include <atomic>
 
 #include "oracle_common.h"
+#include "thirdparty_math.h"
 
 namespace {
 
-struct Quat {
-  double w, x, y, z;
-};
-struct Vec3 {
-  double x, y, z;
-};
-
-/* Eigen quaternion product (Eigen/src/Geometry/Quaternion.h, quat_product<..., double>). */
-inline Quat quatMul(const Quat& a, const Quat& b) {
-  Quat r;
-  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
-  return r;
-}
-
-inline Vec3 cross(const Vec3& a, const Vec3& b) {
-  Vec3 r;
-  r.x = a.y * b.z - a.z * b.y;
-  r.y = a.z * b.x - a.x * b.z;
-  r.z = a.x * b.y - a.y * b.x;
-  return r;
-}
-
-/* Eigen QuaternionBase::_transformVector: uv = q.vec x v; uv += uv; v + q.w*uv + q.vec x uv. */
-inline Vec3 quatRotate(const Quat& q, const Vec3& v) {
-  const Vec3 qv = {q.x, q.y, q.z};
-  Vec3 uv = cross(qv, v);
-  uv.x += uv.x;
-  uv.y += uv.y;
-  uv.z += uv.z;
-  const Vec3 c = cross(qv, uv);
-  Vec3 r;
-  r.x = (v.x + q.w * uv.x) + c.x;
-  r.y = (v.y + q.w * uv.y) + c.y;
-  r.z = (v.z + q.w * uv.z) + c.z;
-  return r;
-}
-
-/* kindr::minimal::QuatTransformation (unit quaternion q_A_B + translation A_t_A_B). */
-struct Transformation {
-  Quat q;
-  Vec3 t;
-  /* transform(p) = q.rotate(p) + t */
-  Vec3 transform(const Vec3& p) const {
-    const Vec3 r = quatRotate(q, p);
-    Vec3 o = {r.x + t.x, r.y + t.y, r.z + t.z};
-    return o;
-  }
-  /* inverse() = (q^-1, -(q^-1).rotate(t)); unit quaternion => inverse = conjugate. */
-  Transformation inverse() const {
-    Transformation o;
-    o.q.w = q.w;
-    o.q.x = -q.x;
-    o.q.y = -q.y;
-    o.q.z = -q.z;
-    const Vec3 r = quatRotate(o.q, t);
-    o.t.x = -r.x;
-    o.t.y = -r.y;
-    o.t.z = -r.z;
-    return o;
-  }
-  /* A * B = (qA*qB, tA + qA.rotate(tB)) */
-  Transformation operator*(const Transformation& rhs) const {
-    Transformation o;
-    o.q = quatMul(q, rhs.q);
-    const Vec3 r = quatRotate(q, rhs.t);
-    o.t.x = t.x + r.x;
-    o.t.y = t.y + r.y;
-    o.t.z = t.z + r.z;
-    return o;
-  }
-};
-
-inline Transformation poseFromRow(const double* r) { /* x y z qw qx qy qz, aerial-mapper-io.cc:110 */
-  Transformation T;
-  T.t.x = r[0];
-  T.t.y = r[1];
-  T.t.z = r[2];
-  T.q.w = r[3];
-  T.q.x = r[4];
-  T.q.y = r[5];
-  T.q.z = r[6];
-  return T;
-}
-
-inline Transformation cameraExtrinsics(const amb_camera& cam) {
-  Transformation T;
-  T.q.w = cam.q_C_B[0];
-  T.q.x = cam.q_C_B[1];
-  T.q.y = cam.q_C_B[2];
-  T.q.z = cam.q_C_B[3];
-  T.t.x = cam.t_C_B[0];
-  T.t.y = cam.t_C_B[1];
-  T.t.z = cam.t_C_B[2];
-  return T;
-}
-
-enum ProjectionStatus { KEYPOINT_VISIBLE, KEYPOINT_OUTSIDE_IMAGE_BOX, POINT_BEHIND_CAMERA, PROJECTION_INVALID };
-
-/* aslam::PinholeCamera::project3Functional + evaluateProjectionResult (kMinimumDepth = 1e-10). */
-inline ProjectionStatus project3(const amb_camera& cam, const Vec3& p, double* kx, double* ky) {
-  const double rz = 1.0 / p.z;
-  double x = p.x * rz;
-  double y = p.y * rz;
-  if (cam.dist_type == AMB_DIST_RADTAN) {
-    /* aslam::RadTanDistortion::distortUsingExternalCoefficients */
-    const double k1 = cam.dist[0], k2 = cam.dist[1], p1 = cam.dist[2], p2 = cam.dist[3];
-    const double mx2_u = x * x;
-    const double my2_u = y * y;
-    const double mxy_u = x * y;
-    const double rho2_u = mx2_u + my2_u;
-    const double rad_dist_u = k1 * rho2_u + k2 * rho2_u * rho2_u;
-    x += x * rad_dist_u + 2.0 * p1 * mxy_u + p2 * (rho2_u + 2.0 * mx2_u);
-    y += y * rad_dist_u + 2.0 * p2 * mxy_u + p1 * (rho2_u + 2.0 * my2_u);
-  } else if (cam.dist_type == AMB_DIST_EQUIDISTANT) {
-    /* aslam::EquidistantDistortion::distortUsingExternalCoefficients */
-    const double k1 = cam.dist[0], k2 = cam.dist[1], k3 = cam.dist[2], k4 = cam.dist[3];
-    const double x2 = x * x;
-    const double y2 = y * y;
-    const double r = std::sqrt(x2 + y2);
-    if (r > 1e-8) {
-      const double theta = std::atan(r);
-      const double theta2 = theta * theta;
-      const double theta4 = theta2 * theta2;
-      const double theta6 = theta4 * theta2;
-      const double theta8 = theta4 * theta4;
-      const double thetad = theta * (1.0 + k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8);
-      const double scaling = thetad / r;
-      x *= scaling;
-      y *= scaling;
-    }
-  }
-  *kx = cam.fu * x + cam.cu;
-  *ky = cam.fv * y + cam.cv;
-  const bool visibility = (*kx >= 0.0) && (*ky >= 0.0) && (*kx < static_cast<double>(cam.width)) &&
-                          (*ky < static_cast<double>(cam.height));
-  if (visibility && (p.z > 1e-10)) return KEYPOINT_VISIBLE;
-  if (!visibility && (p.z > 1e-10)) return KEYPOINT_OUTSIDE_IMAGE_BOX;
-  if (p.z < 0.0) return POINT_BEHIND_CAMERA;
-  return PROJECTION_INVALID;
-}
+using namespace ambo::tp; /* Quat, Vec3, Transformation, project3, ... : the absent dependencies' arithmetic */
 
 /* ortho-backward-grid.cc:164-171 */
 inline bool keypointVisible(const amb_camera& cam, ProjectionStatus st, double kx, double ky) {
@@ -171,16 +25,12 @@ inline bool keypointVisible(const amb_camera& cam, ProjectionStatus st, double k
 
 inline uint32_t packColor(uint8_t b, uint8_t g, uint8_t r) {
   /* ortho-backward-grid.cc:196-201: Eigen::Vector3f(float(rgb[2])/255.0, float(rgb[1])/255.0,
-   * float(rgb[0])/255.0) — float / double literal evaluates in double, stored as float.
-   * grid_map::colorVectorToValue(Vector3f): Vector3i = (v * 255.0).cast<int>() (float product, truncation), then
-   * (t0 << 16) | (t1 << 8) | t2 reinterpreted as float. */
+   * float(rgb[0])/255.0) — float / double literal evaluates in double, stored as float; then
+   * grid_map::colorVectorToValue (thirdparty_math.h). */
   const float fr = static_cast<float>(static_cast<double>(static_cast<float>(r)) / 255.0);
   const float fg = static_cast<float>(static_cast<double>(static_cast<float>(g)) / 255.0);
   const float fb = static_cast<float>(static_cast<double>(static_cast<float>(b)) / 255.0);
-  const int t0 = static_cast<int>(fr * 255.0f);
-  const int t1 = static_cast<int>(fg * 255.0f);
-  const int t2 = static_cast<int>(fb * 255.0f);
-  return (static_cast<uint32_t>(t0) << 16) | (static_cast<uint32_t>(t1) << 8) | static_cast<uint32_t>(t2);
+  return colorVectorToBits(fr, fg, fb);
 }
 
 }  // namespace

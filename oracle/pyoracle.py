@@ -3,8 +3,10 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module
 (see oracle/amb_oracle.h).  The product package `aerial_mapper_b200` never does.
 
-PARITY UNPINNED: the reference holds no golden vectors for this path; see amb_oracle.h for what
-pins the oracle instead.
+Pinning (details in amb_oracle.h): the reference holds no golden vectors for this path; the
+oracle is pinned to oracle/_ref — the reference's own dsm.cc / ortho-backward-grid.cc / ortho-from-pcl.cc compiled
+verbatim here (refsrc_* below) and checked bit-for-bit against the restatement.  PARITY UNPINNED only for the
+arithmetic of the absent third-party dependencies (grid_map, aslam_cv2, minkindr), restated in thirdparty_math.h.
 """
 import ctypes as C
 import os
@@ -15,6 +17,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libamb_oracle_ref.so")
+_REFSRC_MAIN_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_main.so")
+_REFSRC_PCL_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_pcl.so")
 _REFERENCE_ROOT = "/root/reference"
 
 
@@ -32,24 +36,13 @@ class Camera(C.Structure):
 
 
 def build(force=False):
-    """Compile liboracle.so (always possible) and oracle/_ref (only where /root/reference exists)."""
-    need = force or not os.path.exists(_LIB_PATH)
-    srcs = ["dsm_oracle.cc", "ortho_oracle.cc", "stereo_oracle.cc", "dsm_cell_loop.h", "oracle_common.h",
-            "amb_oracle.h"]
-    if not need:
-        t = os.path.getmtime(_LIB_PATH)
-        need = any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in srcs)
-    if need:
-        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    """Compile liboracle.so (always possible) and oracle/_ref (only where /root/reference exists).  `make` is
+    incremental; on the GPU box (no /root/reference) the prebuilt oracle/_ref/*.so that travelled are used as is."""
+    flags = ["-B"] if force else []
+    subprocess.check_call(["make", "-C", _HERE] + flags + ["liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(_REFERENCE_ROOT):
-        need_ref = force or not os.path.exists(_REF_PATH)
-        if not need_ref:
-            t = os.path.getmtime(_REF_PATH)
-            need_ref = any(os.path.getmtime(os.path.join(_HERE, s)) > t
-                           for s in ["ref_nanoflann_dsm.cc", "dsm_cell_loop.h", "oracle_common.h"])
-        if need_ref:
-            subprocess.check_call(["make", "-C", _HERE, "-B", "ref"], stdout=subprocess.DEVNULL,
-                                  stderr=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE] + flags + ["ref"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
 
 
 _lib = None
@@ -111,6 +104,43 @@ def ref():
         L.ambo_ref_ortho_from_pcl_process.restype = C.c_int
         _ref = L
     return _ref
+
+
+_refsrc = None
+
+
+def have_refsrc():
+    if os.path.isdir(_REFERENCE_ROOT):
+        build()
+    return os.path.exists(_REFSRC_MAIN_PATH) and os.path.exists(_REFSRC_PCL_PATH)
+
+
+def refsrc():
+    """oracle/_ref: the reference's OWN dsm.cc, ortho-backward-grid.cc (main) and ortho-from-pcl.cc (pcl) compiled
+    verbatim against the stand-in third-party headers (refsrc_stubs/).  Returns (main, pcl) or None."""
+    global _refsrc
+    if _refsrc is None:
+        if not have_refsrc():
+            return None
+        M = C.CDLL(_REFSRC_MAIN_PATH)
+        M.ambo_refsrc_dsm_process.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32,
+                                              C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
+        M.ambo_refsrc_dsm_process.restype = C.c_int
+        M.ambo_refsrc_ortho_process.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_void_p,
+                                                C.c_size_t, C.c_int32, C.c_size_t, C.c_int32, C.c_int32, C.c_int64,
+                                                C.c_int64, C.c_void_p]
+        M.ambo_refsrc_ortho_process.restype = C.c_int
+        M.ambo_refsrc_last_error.restype = C.c_char_p
+        M.ambo_refsrc_hardware_concurrency.restype = C.c_int
+        P = C.CDLL(_REFSRC_PCL_PATH)
+        P.ambo_refsrc_ortho_from_pcl_process.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.c_size_t, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                                         C.c_void_p]
+        P.ambo_refsrc_ortho_from_pcl_process.restype = C.c_int
+        P.ambo_refsrc_pcl_last_error.restype = C.c_char_p
+        _refsrc = (M, P)
+    return _refsrc
 
 
 def make_geometry(rows, cols, resolution, pos_x=0.0, pos_y=0.0):
@@ -240,3 +270,63 @@ def pack_color(b, g, r):
 
 def hardware_concurrency():
     return int(lib().ambo_hardware_concurrency())
+
+
+# ---- the reference's own translation units (oracle/_ref/libamb_refsrc_*.so) ------------------------------------
+def refsrc_dsm_process(geom, elevation, xyz, radius=1, center_easting=0.0, center_northing=0.0, multi_thread=True,
+                       cell_range=None):
+    """dsm::Dsm(settings, &map).process(cloud, &map) — the reference's dsm.cc.  Returns (status, seconds[2])."""
+    assert elevation.dtype == np.float32 and elevation.flags.f_contiguous
+    assert elevation.shape == (geom.rows, geom.cols)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n = xyz.shape[0] if xyz.ndim == 2 else xyz.size // 3
+    lo, hi = (0, geom.rows * geom.cols) if cell_range is None else cell_range
+    sec = np.zeros(2, np.float64)
+    st = refsrc()[0].ambo_refsrc_dsm_process(C.byref(geom), _ptr(elevation), _ptr(xyz), n, int(radius),
+                                             float(center_easting), float(center_northing),
+                                             1 if multi_thread else 0, lo, hi, _ptr(sec))
+    return st, sec
+
+
+def refsrc_ortho_process(geom, layers, camera, T_G_B, images, colored=False, multi_thread=True, cell_range=None):
+    """ortho::OrthoBackwardGrid(ncameras, settings, &map).process(T_G_Bs, images, &map) — the reference's
+    ortho-backward-grid.cc.  layers as for ortho_process, plus optional "num_observations".
+    Returns (status, seconds[2])."""
+    T = np.ascontiguousarray(T_G_B, dtype=np.float64).reshape(-1, 7)
+    n = T.shape[0]
+    assert len(images) == n
+    imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    channels = 3 if colored else 1
+    row_step = camera.width * channels
+    for im in imgs:
+        assert im.shape[:2] == (camera.height, camera.width)
+        assert (im.ndim == 3 and im.shape[2] == 3) if colored else im.ndim == 2
+    ptrs = (C.c_void_p * max(n, 1))(*[im.ctypes.data for im in imgs])
+    lo, hi = (0, geom.rows * geom.cols) if cell_range is None else cell_range
+    for k in ("elevation", "elevation_angle", "observation_index"):
+        a = layers[k]
+        assert a.dtype == np.float32 and a.flags.f_contiguous and a.shape == (geom.rows, geom.cols), k
+    sec = np.zeros(2, np.float64)
+    st = refsrc()[0].ambo_refsrc_ortho_process(
+        C.byref(geom), _ptr(layers["elevation"]), _ptr(layers["elevation_angle"]),
+        _ptr(layers["observation_index"]), _ptr(layers.get("num_observations")), _ptr(layers.get("ortho")),
+        _ptr(layers.get("colored_ortho")), C.byref(camera), _ptr(T), C.cast(ptrs, C.c_void_p), n, channels, row_step,
+        1 if colored else 0, 1 if multi_thread else 0, lo, hi, _ptr(sec))
+    return st, sec
+
+
+def refsrc_ortho_from_pcl_process(geom, ortho, xyz, intensities, radius=2, adaptive=False, cell_range=None):
+    """ortho::OrthoFromPcl(settings).process(cloud, intensities, &map) — the reference's ortho-from-pcl.cc."""
+    assert ortho.dtype == np.float32 and ortho.flags.f_contiguous and ortho.shape == (geom.rows, geom.cols)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    inten = np.ascontiguousarray(intensities, dtype=np.int32)
+    n = xyz.size // 3
+    assert inten.size >= n
+    lo, hi = (0, geom.rows * geom.cols) if cell_range is None else cell_range
+    return refsrc()[1].ambo_refsrc_ortho_from_pcl_process(C.byref(geom), _ptr(ortho), _ptr(xyz), _ptr(inten), n,
+                                                          int(radius), 1 if adaptive else 0, lo, hi, None)
+
+
+def refsrc_last_error():
+    M, P = refsrc()
+    return (M.ambo_refsrc_last_error() or b"").decode(), (P.ambo_refsrc_pcl_last_error() or b"").decode()

@@ -1,9 +1,11 @@
 """Generate the committed golden fixtures (small seeded inputs -> oracle outputs).
 
-PARITY UNPINNED at the source: the reference has no golden vectors for this path, so these are
-outputs of THIS repository's oracle.  The DSM fixture is produced with oracle/_ref (the reference's own
-nanoflann.hpp compiled verbatim + restated loop) when /root/reference is present, which is how it was generated
-for the committed files; the portable restatement must reproduce it bit for bit (tests/test_golden.py).
+The reference has no golden vectors for this path, so these are outputs of THIS repository's
+oracle — the DSM one produced with oracle/_ref (the reference's own nanoflann.hpp compiled verbatim + restated loop,
+which also records neighbour counts and retry levels) when /root/reference is present, which is how the committed
+files were generated.  tests/test_oracle_refsrc.py then checks that the reference's OWN dsm.cc and
+ortho-backward-grid.cc (compiled verbatim into oracle/_ref) reproduce every committed layer bit for bit, and
+tests/test_golden.py that the portable restatement does.
 
     python tests/golden/make_golden.py
 """
