@@ -230,3 +230,56 @@ def test_golden_fixtures_are_bit_for_bit_what_the_reference_sources_produce():
         assert np.array_equal(L["elevation_angle"].view(np.uint32), z["elevation_angle"].view(np.uint32))
         assert np.array_equal(L["observation_index"].view(np.uint32), z["observation_index"].view(np.uint32))
         assert np.array_equal(L["colored_ortho" if colored else "ortho"].view(np.uint32), z["out"])
+
+
+# ---- randomised (hypothesis): any geometry / offset / camera — the restatement is the reference's code, bit for bit --
+from hypothesis import given, settings, strategies as hst  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=hst.integers(0, 100_000), rows=hst.integers(3, 40), cols=hst.integers(3, 40),
+       res=hst.sampled_from([0.1, 0.25, 0.4, 0.5, 1.0, 2.0]), radius=hst.integers(1, 9),
+       pos_x=hst.floats(-500.0, 500.0), pos_y=hst.floats(-500.0, 500.0),
+       ce=hst.floats(-50.0, 50.0), cn=hst.floats(-50.0, 50.0), density=hst.sampled_from([0.05, 0.5, 4.0]))
+def test_random_dsm_cases_bit_identical_to_reference_dsm_cc(seed, rows, cols, res, radius, pos_x, pos_y, ce, cn,
+                                                          density):
+    n = max(1, int(density * rows * res * cols * res))
+    rng = np.random.default_rng(seed)
+    xyz = np.c_[rng.uniform(-rows * res / 2 - 2, rows * res / 2 + 2, n) + pos_x + cn,
+                rng.uniform(-cols * res / 2 - 2, cols * res / 2 + 2, n) + pos_y + ce,
+                rng.normal(100.0, 5.0, n)]
+    g = po.make_geometry(rows, cols, res, pos_x, pos_y)
+    a, b, c = _nan_layer(rows, cols), _nan_layer(rows, cols), _nan_layer(rows, cols)
+    st, _ = po.refsrc_dsm_process(g, a, xyz, radius, ce, cn, multi_thread=bool(seed & 1))
+    assert st == 0, po.refsrc_last_error()
+    assert po.dsm_process(g, b, xyz, radius, ce, cn, num_threads=-1, use_ref=True)[0] == 0
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    st, _, lvl, _ = po.dsm_process(g, c, xyz, radius, ce, cn, num_threads=-1, debug=True)
+    assert st == 0
+    assert np.array_equal(np.isnan(a), lvl < 0) and ulp_diff(a, c).max() <= 1
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=hst.integers(0, 100_000), rows=hst.integers(4, 36), cols=hst.integers(4, 36),
+       res=hst.sampled_from([0.25, 0.5, 1.0]), dist_type=hst.integers(0, 2), colored=hst.booleans(),
+       agl=hst.floats(20.0, 120.0), tilt=hst.floats(0.0, 25.0), n_frames=hst.integers(1, 7))
+def test_random_ortho_cases_bit_identical_to_reference_ortho_backward_grid_cc(seed, rows, cols, res, dist_type,
+                                                                             colored, agl, tilt, n_frames):
+    dist = {0: (0, 0, 0, 0), 1: RADTAN, 2: EQUI}[dist_type]
+    camd = synth.scaled_camera(0.03, dist_type=dist_type, dist=dist)
+    rng = np.random.default_rng(seed)
+    q = np.r_[1.0, rng.normal(0, 0.05, 3)]
+    camd["q_C_B"], camd["t_C_B"] = tuple(q / np.linalg.norm(q)), tuple(rng.normal(0, 0.1, 3))
+    poses = synth.lawnmower_poses(1, n_frames, rows * res / 2, cols * res / 2, agl, seed=seed, jitter_pos=1.0,
+                                  jitter_rp_deg=tilt)
+    ch = 3 if colored else 1
+    imgs = [synth.procedural_image(k, camd["width"], camd["height"], ch) for k in range(n_frames)]
+    elev = synth.analytic_elevation(rows, cols, res)
+    elev[rng.integers(0, rows), rng.integers(0, cols)] = np.nan
+    g, cam = po.make_geometry(rows, cols, res), po.make_camera(**camd)
+    A, B = fresh_layers(rows, cols, elev), fresh_layers(rows, cols, elev)
+    st, _ = po.refsrc_ortho_process(g, A, cam, poses, imgs, colored=colored, multi_thread=bool(seed & 1))
+    assert st == 0, po.refsrc_last_error()
+    assert po.ortho_process(g, B, cam, poses, imgs, colored=colored, num_threads=-1)[0] == 0
+    for k in ("elevation_angle", "observation_index", "ortho", "colored_ortho"):
+        assert np.array_equal(A[k].view(np.uint32), B[k].view(np.uint32)), k
