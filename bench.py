@@ -336,18 +336,25 @@ def run_ours(args):
     alg_bytes = DSM_BYTES_PER_POINT * n_rank_points + DSM_BYTES_PER_CELL * stripe_cells
     g_ms = float(np.mean(gather_ms))
     achieved = alg_bytes / (g_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, compute_note = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             if world == 1:
-                traffic = json.load(f)[args.workload]["dsm_gather_kernel"]["traffic_bytes_per_launch"]
+                cap = json.load(f)[args.workload]["dsm_gather_kernel"]
+                traffic = cap["traffic_bytes_per_launch"]
+                if "fp64_pipe_active_pct" in cap:  # same capture: why the HBM fraction is low
+                    compute_note = {"fp64_pipe_active_pct": cap["fp64_pipe_active_pct"],
+                                    "issue_active_pct": cap.get("issue_active_pct"),
+                                    "source": cap.get("compute_source")}
     except Exception:
-        traffic = None
+        traffic, compute_note = None, None
     roofline = {"bound": "hbm", "kernel": "dsm_gather_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": g_ms,
                 "stage_ms": {"dsm_bin": float(np.mean(bin_ms)), "dsm_gather": g_ms,
                              "dsm_fill": float(np.mean(fill_ms)), "ortho": float(np.mean(ortho_ms))}}
+    if compute_note is not None:
+        roofline["compute_capture"] = compute_note
     out = {"metric": "grid cells/sec (DSM+ortho)", "value": value, "unit": "cells/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
