@@ -19,6 +19,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libamb_oracle_ref.so")
 _REFSRC_MAIN_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_main.so")
 _REFSRC_PCL_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_pcl.so")
+_REFERENCE_DEMO_PATH = os.path.join(_HERE, "_ref", "libamb_reference_demo.so")
 _REFERENCE_ROOT = "/root/reference"
 
 
@@ -141,6 +142,23 @@ def refsrc():
         P.ambo_refsrc_pcl_last_error.restype = C.c_char_p
         _refsrc = (M, P)
     return _refsrc
+
+
+def have_reference_demo():
+    if os.path.isdir(_REFERENCE_ROOT):
+        build()
+    return os.path.exists(_REFERENCE_DEMO_PATH)
+
+
+def reference_demo_main(*argv):
+    """tests/cpp/shim_demo.cc (the batch demo's call sequence) built against the reference's own headers + sources:
+    runs its main(argc, argv) in-process and returns its exit code."""
+    L = C.CDLL(_REFERENCE_DEMO_PATH)
+    L.amb_demo_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.amb_demo_main.restype = C.c_int
+    args = [b"reference_demo"] + [os.fsencode(a) for a in argv]
+    arr = (C.c_char_p * (len(args) + 1))(*args, None)
+    return L.amb_demo_main(len(args), arr)
 
 
 def make_geometry(rows, cols, resolution, pos_x=0.0, pos_y=0.0):

@@ -22,6 +22,11 @@
  *
  * Extensions the glue needs (prefixed amb*): GridMap wraps caller-owned layer buffers and can restrict
  * GridMapIterator to a linear-index sub-range (the bench's bounded sample).
+ * The stand-ins also carry the CALLER-side members the reference's demos use to set a job up (GridMap(layers) +
+ * setGeometry + setConstant, aslam::Camera/Distortion/NCamera constructors, Pose(w,x,y,z,t), owning cv::Mat), with
+ * the same spelling as aerial_mapper_b200/shim/mini/amb_mini_deps.h, so that ONE caller source
+ * (tests/cpp/shim_demo.cc = the batch demo's call sequence) builds against the reference's headers + sources here
+ * and against the drop-in headers + CUDA library there (tests/test_shim.py).
  * glog FATAL (a failed CHECK) throws ambref::CheckFailed instead of aborting; on a worker thread of utils::parFor
  * that terminates the process, exactly like the reference's abort.
  */
@@ -162,19 +167,31 @@ typedef Eigen::Array2i Size;
 typedef Eigen::Vector2d Position;
 typedef Eigen::Vector2d Length;
 
-/* grid_map::Matrix = Eigen::MatrixXf: column-major float32; here a view of the caller's buffer. */
+/* grid_map::Matrix = Eigen::MatrixXf: column-major float32; a view of the caller's buffer (glue) or owning (demo). */
 class Matrix {
  public:
   Matrix() : data_(nullptr), rows_(0), cols_(0) {}
   Matrix(float* data, Eigen::Index rows, Eigen::Index cols) : data_(data), rows_(rows), cols_(cols) {}
+  void resize(Eigen::Index rows, Eigen::Index cols) {
+    own_.reset(new std::vector<float>(static_cast<size_t>(rows) * static_cast<size_t>(cols), 0.0f));
+    data_ = own_->data();
+    rows_ = rows;
+    cols_ = cols;
+  }
+  void setConstant(float value) {
+    for (Eigen::Index k = 0; k < rows_ * cols_; ++k) data_[k] = value;
+  }
   float& operator()(Eigen::Index i, Eigen::Index j) { return data_[j * rows_ + i]; }
   const float& operator()(Eigen::Index i, Eigen::Index j) const { return data_[j * rows_ + i]; }
+  float* data() { return data_; }
+  const float* data() const { return data_; }
   Eigen::Index rows() const { return rows_; }
   Eigen::Index cols() const { return cols_; }
 
  private:
   float* data_;
   Eigen::Index rows_, cols_;
+  std::shared_ptr<std::vector<float> > own_;
 };
 
 class GridMap {
@@ -183,6 +200,34 @@ class GridMap {
     size_ = Size(g.rows, g.cols);
     iter_end_ = static_cast<int64_t>(g.rows) * g.cols;
   }
+  /* caller side, as the demos use it (aerial-mapper-grid-map.cc:23-33) */
+  explicit GridMap(const std::vector<std::string>& layers) : iter_begin_(0), iter_end_(0) {
+    std::memset(&geometry_, 0, sizeof(geometry_));
+    size_ = Size(0, 0);
+    for (size_t k = 0; k < layers.size(); ++k) layers_[layers[k]];
+  }
+  void setFrameId(const std::string& frame_id) { frame_id_ = frame_id; }
+  const std::string& getFrameId() const { return frame_id_; }
+  /* grid_map::GridMap::setGeometry: size = round(length / resolution), length = size * resolution, every layer
+   * resized and set to NaN (clearAll), startIndex = 0. */
+  void setGeometry(const Length& length, double resolution, const Position& position) {
+    geometry_.rows = static_cast<int32_t>(std::round(length(0) / resolution));
+    geometry_.cols = static_cast<int32_t>(std::round(length(1) / resolution));
+    geometry_.resolution = resolution;
+    geometry_.length_x = geometry_.rows * resolution;
+    geometry_.length_y = geometry_.cols * resolution;
+    geometry_.pos_x = position(0);
+    geometry_.pos_y = position(1);
+    size_ = Size(geometry_.rows, geometry_.cols);
+    iter_begin_ = 0;
+    iter_end_ = static_cast<int64_t>(geometry_.rows) * geometry_.cols;
+    for (std::unordered_map<std::string, Matrix>::iterator it = layers_.begin(); it != layers_.end(); ++it) {
+      it->second.resize(geometry_.rows, geometry_.cols);
+      it->second.setConstant(std::nanf(""));
+    }
+  }
+  Length getLength() const { return Length(geometry_.length_x, geometry_.length_y); }
+  Position getPosition() const { return Position(geometry_.pos_x, geometry_.pos_y); }
   /* amb* = glue-only extensions */
   void ambAddLayer(const std::string& name, float* data) {
     layers_[name] = Matrix(data, geometry_.rows, geometry_.cols);
@@ -216,6 +261,7 @@ class GridMap {
   Size size_;
   std::unordered_map<std::string, Matrix> layers_;
   int64_t iter_begin_, iter_end_;
+  std::string frame_id_;
 };
 
 /* grid_map::GridMapIterator: linear index over the column-major buffer, index = (k % rows, k / rows)
@@ -255,6 +301,30 @@ class QuatTransformation {
     T_.t.x = T_.t.y = T_.t.z = 0.0;
   }
   explicit QuatTransformation(const ambo::tp::Transformation& T) : T_(T) {}
+  /* caller side: unit quaternion (w, x, y, z) + translation, the order of aerial-mapper-io.cc:110-117 */
+  QuatTransformation(double w, double x, double y, double z, double tx, double ty, double tz) {
+    T_.q.w = w;
+    T_.q.x = x;
+    T_.q.y = y;
+    T_.q.z = z;
+    T_.t.x = tx;
+    T_.t.y = ty;
+    T_.t.z = tz;
+  }
+  struct RotationQuaternion {
+    ambo::tp::Quat q;
+    double w() const { return q.w; }
+    double x() const { return q.x; }
+    double y() const { return q.y; }
+    double z() const { return q.z; }
+  };
+  RotationQuaternion getRotation() const {
+    RotationQuaternion r;
+    r.q = T_.q;
+    return r;
+  }
+  Eigen::Vector3d getPosition() const { return Eigen::Vector3d(T_.t.x, T_.t.y, T_.t.z); }
+  const ambo::tp::Transformation& ambTransformation() const { return T_; }
   QuatTransformation inverse() const { return QuatTransformation(T_.inverse()); }
   Eigen::Vector3d transform(const Eigen::Vector3d& p) const {
     const ambo::tp::Vec3 in = {p(0), p(1), p(2)};
@@ -283,10 +353,50 @@ struct ProjectionResult {
   Status status_;
 };
 
+class Distortion {
+ public:
+  enum class Type { kNoDistortion = 0, kEquidistant = 1, kFisheye = 2, kRadTan = 3 };
+  Distortion(Type type, const Eigen::Vector4d& parameters) : type_(type), parameters_(parameters) {}
+  Type getType() const { return type_; }
+  const Eigen::Vector4d& getParameters() const { return parameters_; }
+
+ private:
+  Type type_;
+  Eigen::Vector4d parameters_;
+};
+
 /* aslam::PinholeCamera with its distortion, as one concrete class (the reference only calls through Camera&). */
 class Camera {
  public:
-  explicit Camera(const amb_camera& c) : c_(c) {}
+  explicit Camera(const amb_camera& c) : c_(c), intrinsics_(), distortion_(Distortion::Type::kNoDistortion, Eigen::Vector4d()) {
+    for (int k = 0; k < 4; ++k) distortion_params_(k) = c.dist[k];
+    intrinsics_(0) = c.fu;
+    intrinsics_(1) = c.fv;
+    intrinsics_(2) = c.cu;
+    intrinsics_(3) = c.cv;
+    const Distortion::Type t = c.dist_type == AMB_DIST_RADTAN        ? Distortion::Type::kRadTan
+                               : c.dist_type == AMB_DIST_EQUIDISTANT ? Distortion::Type::kEquidistant
+                                                                     : Distortion::Type::kNoDistortion;
+    distortion_ = Distortion(t, distortion_params_);
+  }
+  /* caller side: PinholeCamera(intrinsics fu fv cu cv, width, height, distortion) */
+  Camera(unsigned width, unsigned height, const Eigen::Vector4d& intrinsics, const Distortion& distortion)
+      : intrinsics_(intrinsics), distortion_(distortion) {
+    std::memset(&c_, 0, sizeof(c_));
+    c_.width = static_cast<int32_t>(width);
+    c_.height = static_cast<int32_t>(height);
+    c_.fu = intrinsics(0);
+    c_.fv = intrinsics(1);
+    c_.cu = intrinsics(2);
+    c_.cv = intrinsics(3);
+    c_.dist_type = distortion.getType() == Distortion::Type::kRadTan        ? AMB_DIST_RADTAN
+                   : distortion.getType() == Distortion::Type::kEquidistant ? AMB_DIST_EQUIDISTANT
+                                                                            : AMB_DIST_NONE;
+    for (int k = 0; k < 4; ++k) c_.dist[k] = distortion.getParameters()(k);
+    c_.q_C_B[0] = 1.0;
+  }
+  const Eigen::Vector4d& getParameters() const { return intrinsics_; }
+  const Distortion& getDistortion() const { return distortion_; }
   const ProjectionResult project3(const Eigen::Vector3d& point_3d, Eigen::Vector2d* out_keypoint) const {
     const ambo::tp::Vec3 p = {point_3d(0), point_3d(1), point_3d(2)};
     double kx, ky;
@@ -309,6 +419,8 @@ class Camera {
 
  private:
   amb_camera c_;
+  Eigen::Vector4d intrinsics_, distortion_params_;
+  Distortion distortion_;
 };
 typedef Camera PinholeCamera;
 
@@ -316,6 +428,7 @@ class NCamera {
  public:
   typedef std::shared_ptr<NCamera> Ptr;
   explicit NCamera(const amb_camera& c) : camera_(c), T_C_B_(ambo::tp::cameraExtrinsics(c)) {}
+  NCamera(const Camera& camera, const Transformation& T_C_B) : camera_(camera), T_C_B_(T_C_B) {}  /* caller side */
   const Camera& getCamera(size_t /*camera_index*/) const { return camera_; }
   const Transformation& get_T_C_B(size_t /*camera_index*/) const { return T_C_B_; }
 
@@ -333,19 +446,31 @@ struct Vec3b {
   const uchar& operator[](int i) const { return val[i]; }
   uchar& operator[](int i) { return val[i]; }
 };
-/* cv::Mat as a view of the caller's interleaved uint8 image. */
+/* cv::Mat: interleaved uint8 image; a view of the caller's buffer (glue) or owning (demo). */
 class Mat {
  public:
-  Mat() : rows(0), cols(0), data(nullptr), step(0) {}
-  Mat(int rows_, int cols_, const uchar* data_, size_t step_) : rows(rows_), cols(cols_), data(data_), step(step_) {}
+  Mat() : rows(0), cols(0), data(nullptr), step(0), channels_(1) {}
+  Mat(int rows_, int cols_, const uchar* data_, size_t step_)
+      : rows(rows_), cols(cols_), data(const_cast<uchar*>(data_)), step(step_),
+        channels_(cols_ > 0 ? static_cast<int>(step_ / static_cast<size_t>(cols_)) : 1) {}
+  Mat(int rows_, int cols_, int channels)
+      : rows(rows_), cols(cols_), data(nullptr), step(static_cast<size_t>(cols_) * channels), channels_(channels) {
+    own_.reset(new std::vector<uchar>(static_cast<size_t>(rows_) * step));
+    data = own_->data();
+  }
   template <typename T>
   const T& at(int row, int col) const {
     return *reinterpret_cast<const T*>(data + static_cast<size_t>(row) * step + static_cast<size_t>(col) * sizeof(T));
   }
   bool empty() const { return data == nullptr; }
+  int channels() const { return channels_; }
   int rows, cols;
-  const uchar* data;
+  uchar* data;
   size_t step;
+
+ private:
+  int channels_;
+  std::shared_ptr<std::vector<uchar> > own_;
 };
 }  // namespace cv
 

@@ -1,8 +1,18 @@
-// shim_demo.cc — the call sequence of the reference's batch demo (main-ortho-backward-grid.cc:119-141) written
-// against the DROP-IN headers (aerial_mapper_b200/shim), with the mini stand-ins for the absent third-party
-// libraries.  Reads a scenario file written by tests/test_gpu_shim.py, writes the resulting layers back.
+// shim_demo.cc — the call sequence of the reference's batch demo (main-ortho-backward-grid.cc:119-141): caller code
+// that only uses the reference's public API.  ONE source, two builds (tests/test_shim.py):
+//   * against the DROP-IN headers (aerial_mapper_b200/shim, -DAMB_SHIM_MINI stand-ins) + libaerial_mapper_b200.so
+//     -> the CUDA path;
+//   * against the REFERENCE'S OWN headers and sources (dsm.cc, ortho-backward-grid.cc compiled verbatim from
+//     /root/reference with oracle/refsrc_stubs) -> oracle/_ref/libamb_reference_demo.so, the CPU path
+//     (-DAMB_DEMO_AS_LIBRARY: main() gets a C name so the test can call it through ctypes).
+// Reads a scenario file written by the test, writes the resulting layers back.
 #include <aerial-mapper-dsm/dsm.h>
 #include <aerial-mapper-ortho/ortho-backward-grid.h>
+
+#ifdef AMB_DEMO_AS_LIBRARY
+extern "C" __attribute__((visibility("default"))) int amb_demo_main(int argc, char** argv);
+#define main amb_demo_main
+#endif
 
 #include <cstdio>
 #include <fstream>

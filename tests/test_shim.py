@@ -1,6 +1,11 @@
 """The C++ drop-in headers (aerial_mapper_b200/shim: dsm::Dsm, ortho::OrthoBackwardGrid with the reference's
 signatures) compile against the C ABI; on a GPU the demo's call sequence through them gives the same layers as the
-Python mirror."""
+Python mirror.
+
+Source-level drop-in: tests/cpp/shim_demo.cc — caller code that only uses the reference's public API, the batch demo's
+call sequence — is ONE source with two builds: against the drop-in headers + CUDA library (here), and against the
+reference's OWN headers and sources (dsm.cc, ortho-backward-grid.cc compiled verbatim; oracle/_ref/
+libamb_reference_demo.so).  Swapping the include path and the link line is the whole integration."""
 import os
 import subprocess
 
@@ -34,11 +39,10 @@ def test_shim_headers_compile_and_link(tmp_path):
                            "-L" + libdir, "-laerial_mapper_b200", "-Wl,-rpath," + libdir])
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("colored", [False, True])
-def test_demo_sequence_through_the_cpp_shim(tmp_path, colored):
-    exe = build_demo(tmp_path)
-    rows, cols, res = 120, 90, 0.5
+LAYERS = ["elevation", "elevation_angle", "observation_index", "ortho", "colored_ortho"]
+
+
+def make_scenario(tmp_path, colored, rows=120, cols=90, res=0.5):
     xyz = synth.point_cloud(30000, rows * res / 2, cols * res / 2, seed=51, holes=2, hole_sides=(3.0, 9.0))
     camd = synth.scaled_camera(0.06)
     poses = synth.lawnmower_poses(2, 3, rows * res / 2, cols * res / 2, 50.0, seed=52, jitter_pos=0.5)
@@ -53,10 +57,75 @@ def test_demo_sequence_through_the_cpp_shim(tmp_path, colored):
         poses.tofile(f)
         for im in imgs:
             im.tofile(f)
+    return scen, (rows, cols, res, xyz, camd, poses, imgs)
+
+
+def read_layers(path, rows, cols):
+    return np.fromfile(path, np.float32).reshape(5, cols, rows).transpose(0, 2, 1)  # column-major layers
+
+
+def run_reference_demo(tmp_path, scen, rows, cols):
+    from oracle import pyoracle as po
+    out = tmp_path / "layers_reference.bin"
+    assert po.reference_demo_main(str(scen), str(out)) == 0
+    return read_layers(out, rows, cols)
+
+
+@pytest.mark.parametrize("colored", [False, True])
+def test_same_demo_source_runs_on_the_reference_sources(tmp_path, colored):
+    # CPU: the demo source built against the reference's own dsm.cc / ortho-backward-grid.cc gives, bit for bit, what
+    # the reference classes give when driven through the oracle glue (and hence what the restated oracle gives)
+    from common import fresh_layers
+    from oracle import pyoracle as po
+    if not po.have_reference_demo():
+        pytest.skip("oracle/_ref/libamb_reference_demo.so not built (needs /root/reference)")
+    scen, (rows, cols, res, xyz, camd, poses, imgs) = make_scenario(tmp_path, colored)
+    got = run_reference_demo(tmp_path, scen, rows, cols)
+    g = po.make_geometry(rows, cols, res)
+    L = fresh_layers(rows, cols)
+    assert po.refsrc_dsm_process(g, L["elevation"], xyz)[0] == 0
+    assert po.refsrc_ortho_process(g, L, po.make_camera(**camd), poses, imgs, colored=colored)[0] == 0
+    for k, name in enumerate(LAYERS):
+        assert np.array_equal(got[k].view(np.uint32), L[name].view(np.uint32)), name
+    assert np.isnan(got[0]).any() and (~np.isnan(got[2])).mean() > 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("colored", [False, True])
+def test_one_demo_source_two_builds_cuda_vs_reference(tmp_path, colored):
+    # the same caller source: drop-in headers + CUDA library vs the reference's headers + sources
+    from common import ulp_diff
+    from oracle import pyoracle as po
+    if not po.have_reference_demo():
+        pytest.skip("oracle/_ref/libamb_reference_demo.so not present")
+    exe = build_demo(tmp_path)
+    scen, (rows, cols, res, xyz, camd, poses, imgs) = make_scenario(tmp_path, colored)
     out = tmp_path / "layers.bin"
     r = subprocess.run([exe, str(scen), str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    got = np.fromfile(out, np.float32).reshape(5, cols, rows).transpose(0, 2, 1)  # column-major layers
+    cuda = read_layers(out, rows, cols)
+    ref = run_reference_demo(tmp_path, scen, rows, cols)
+    assert np.array_equal(np.isnan(cuda[0]), np.isnan(ref[0]))
+    assert ulp_diff(cuda[0], ref[0]).max() <= 1                       # elevation: summation order only
+    # each side's orthomosaic runs on its own elevation; a 1-ulp height difference can move a frame decision only in
+    # a cell where two frames tie to ~1e-8 in observation angle: allow a couple of such cells, everything else exact
+    a, b = cuda[2], ref[2]
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert (~same).sum() <= 2
+    for k in (3, 4):
+        assert (cuda[k].view(np.uint32) != ref[k].view(np.uint32))[same].sum() == 0, LAYERS[k]
+    assert ulp_diff(cuda[1][same], ref[1][same]).max() <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("colored", [False, True])
+def test_demo_sequence_through_the_cpp_shim(tmp_path, colored):
+    exe = build_demo(tmp_path)
+    scen, (rows, cols, res, xyz, camd, poses, imgs) = make_scenario(tmp_path, colored)
+    out = tmp_path / "layers.bin"
+    r = subprocess.run([exe, str(scen), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = read_layers(out, rows, cols)
 
     gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
     amb.Dsm(amb.DsmSettings(), gm).process(xyz, gm)
