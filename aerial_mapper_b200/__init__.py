@@ -7,8 +7,9 @@ from ._lib import (AMB_OK, AmbError, Camera, Geometry, LAYER_ID, LAYER_NAMES, DI
                    DIST_RADTAN, LIB_PATH, build, check, lib)
 from .api import (AerialGridMap, Dsm, DsmSettings, GridMap, GridMapSettings, HOT_LAYERS, NCamera,
                   OrthoBackwardGrid, OrthoFromPcl, OrthoFromPclSettings, OrthoSettings, compute_point_cloud,
-                  dsm_thresholds)
+                  dsm_thresholds, rectify_stereo_maps, rectify_stereo_setup)
 
 __all__ = ["AMB_OK", "AmbError", "Camera", "Geometry", "LAYER_ID", "LAYER_NAMES", "DIST_EQUIDISTANT", "DIST_NONE",
            "DIST_RADTAN", "LIB_PATH", "build", "check", "lib", "AerialGridMap", "Dsm", "DsmSettings", "GridMap",
-           "GridMapSettings", "HOT_LAYERS", "NCamera", "OrthoBackwardGrid", "OrthoFromPcl", "OrthoFromPclSettings", "OrthoSettings", "compute_point_cloud", "dsm_thresholds"]
+           "GridMapSettings", "HOT_LAYERS", "NCamera", "OrthoBackwardGrid", "OrthoFromPcl", "OrthoFromPclSettings", "OrthoSettings", "compute_point_cloud", "dsm_thresholds",
+           "rectify_stereo_maps", "rectify_stereo_setup"]

@@ -89,6 +89,10 @@ SYMBOLS = {
                                        _P, _P, C.c_float, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "amb_stereo_reproject_device": (C.c_int, [C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, C.c_int32, C.c_int32, _P,
                                               C.c_double, _P, _P, C.c_float, _P, _P, C.c_size_t, _P, _P]),
+    "amb_stereo_rectify_setup": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "amb_stereo_rectify_maps": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_int32, C.c_size_t, _P, _P, _P, _P]),
+    "amb_stereo_rectify_maps_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int32, C.c_int32, C.c_size_t, _P, _P, _P, _P,
+                                                 _P]),
     "amb_ortho_process": (C.c_int, [_P, C.POINTER(Camera), _P, _P, C.c_size_t, C.c_int32, C.c_size_t, C.c_int32]),
     "amb_ortho_process_device": (C.c_int, [_P, C.POINTER(Camera), _P, _P, C.c_size_t, C.c_int32, C.c_size_t,
                                            C.c_int32]),

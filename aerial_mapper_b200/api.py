@@ -470,3 +470,30 @@ def compute_point_cloud(disparity_map, image_left, K, baseline, R_G_C, t_G_C1, d
                                      float(max_invalid_disparity), xyz.ctypes.data_as(C.c_void_p),
                                      inten.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
     return xyz[:n.value].copy(), inten[:n.value].copy()
+
+
+def rectify_stereo_setup(K, R_G_C1, R_G_C2, t_G_C1, t_G_C2):
+    """Host half of stereo::Rectifier::rectifyStereoPair (rectifier.cpp:43-79; "next" row N3): Fusiello's compact
+    rectification.  Returns (baseline, R_G_C_rect float64 [3, 3], T1_inv float32 [3, 3], T2_inv float32 [3, 3])."""
+    a = [np.ascontiguousarray(m, dtype=np.float64).reshape(n) for m, n in
+         ((K, 9), (R_G_C1, 9), (R_G_C2, 9), (t_G_C1, 3), (t_G_C2, 3))]
+    baseline = C.c_double(0.0)
+    R = np.zeros(9, np.float64)
+    T1 = np.zeros(9, np.float32)
+    T2 = np.zeros(9, np.float32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    check(lib().amb_stereo_rectify_setup(p(a[0]), p(a[1]), p(a[2]), p(a[3]), p(a[4]), C.byref(baseline), p(R), p(T1),
+                                         p(T2)))
+    return baseline.value, R.reshape(3, 3), T1.reshape(3, 3), T2.reshape(3, 3)
+
+
+def rectify_stereo_maps(T1_inv, T2_inv, width, height, device=0):
+    """Device half (rectifier.cpp:80-104): the four CV_32FC1 rectification maps cv::remap consumes.
+    Returns (map_rectify_1_x, map_rectify_1_y, map_rectify_2_x, map_rectify_2_y), float32 [H, W] each."""
+    T1 = np.ascontiguousarray(T1_inv, dtype=np.float32).reshape(9)
+    T2 = np.ascontiguousarray(T2_inv, dtype=np.float32).reshape(9)
+    maps = [np.empty((int(height), int(width)), np.float32) for _ in range(4)]
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    check(lib().amb_stereo_rectify_maps(int(device), p(T1), p(T2), int(width), int(height), int(width), p(maps[0]),
+                                        p(maps[1]), p(maps[2]), p(maps[3])))
+    return tuple(maps)

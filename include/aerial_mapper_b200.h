@@ -226,6 +226,28 @@ int amb_stereo_reproject_device(int device, void* stream, const float* d_dispari
                                 float max_invalid_disparity, double* d_out_xyz, int32_t* d_out_intensity,
                                 size_t capacity, uint32_t* d_block_scratch, unsigned long long* d_count);
 
+/* ---- "next" row N3, second half: stereo::Rectifier::rectifyStereoPair (aerial_mapper_dense_pcl/src/rectifier.cpp:36-107) ----
+ * The step before block matching in the same pipeline.  Matrices are row-major 3x3 doubles; K is the full camera
+ * matrix (stereo::StereoRigParameters::K, common.h:41).
+ * setup (host arithmetic, no GPU; rectifier.cpp:43-79): Fusiello's compact rectification — baseline = |t_G_C2 - t_G_C1|,
+ * R_G_C_rect (rows = new x/y/z axes; RectifiedStereoPair::R_G_C, what amb_stereo_reproject takes), and the two
+ * rectifying homographies inverted and cast to float32 (T1_inv, T2_inv, 9 floats each, row-major).
+ * A zero baseline or a singular matrix returns AMB_ERR_CHECK_FAILED. */
+int amb_stereo_rectify_setup(const double* K, const double* R_G_C1, const double* R_G_C2, const double* t_G_C1,
+                             const double* t_G_C2, double* baseline, double* R_G_C_rect, float* T1_inv,
+                             float* T2_inv);
+/* maps (rectifier.cpp:80-104): for every rectified pixel, [x y w]^T = T_i_inv [u v 1]^T in float32 and
+ * map_rectify_i = (x / w, y / w) — the four CV_32FC1 maps cv::remap consumes; H x W, row stride map_stride floats.
+ * w == 0 anywhere returns AMB_ERR_CHECK_FAILED (CHECK_NE(xyw(2), 0.0), :92,:99).  cv::remap and the contour mask
+ * (OpenCV) stay with the caller, like block matching. */
+int amb_stereo_rectify_maps(int device, const float* T1_inv, const float* T2_inv, int32_t width, int32_t height,
+                            size_t map_stride, float* map1_x, float* map1_y, float* map2_x, float* map2_y);
+/* Same with device maps on `stream` (a cudaStream_t as void*, may be NULL); T*_inv are HOST pointers (72 bytes of
+ * kernel constants); d_zero_w_flag (nullable, int32 zeroed by the caller) is set to 1 if any w == 0.  Asynchronous. */
+int amb_stereo_rectify_maps_device(int device, void* stream, const float* T1_inv, const float* T2_inv, int32_t width,
+                                   int32_t height, size_t map_stride, float* d_map1_x, float* d_map1_y,
+                                   float* d_map2_x, float* d_map2_y, int32_t* d_zero_w_flag);
+
 /* ---- Orthomosaic: ortho::OrthoBackwardGrid::process (ortho-backward-grid.cc:223-239) ---- */
 /* T_G_B: n poses, 7 doubles each in the order of the reference's pose files: x y z qw qx qy qz
  * (aerial-mapper-io.cc:110).  images: n host pointers to H x W x channels uint8 rasters with `row_step` bytes

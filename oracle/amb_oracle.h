@@ -87,6 +87,15 @@ int ambo_stereo_reproject(const float* disparity, size_t disparity_stride, const
                           const double* R_G_C, const double* t_G_C1, float max_invalid_disparity, double* out_xyz,
                           int32_t* out_intensity, size_t capacity, size_t* out_count);
 
+/* stereo::Rectifier::rectifyStereoPair restated (rectifier.cpp:36-107; "next" row N3, second half).  Matrices row-major
+ * 3x3.  setup: Fusiello rectification in double -> baseline, R_G_C_rect and the two float32 homographies T_i^-1;
+ * maps: the per-pixel fill of the four CV_32FC1 maps (row stride map_stride floats).  remap / mask stay OpenCV. */
+int ambo_stereo_rectify_setup(const double* K, const double* R_G_C1, const double* R_G_C2, const double* t_G_C1,
+                              const double* t_G_C2, double* baseline, double* R_G_C_rect, float* T1_inv,
+                              float* T2_inv);
+int ambo_stereo_rectify_maps(const float* T1_inv, const float* T2_inv, int32_t width, int32_t height,
+                             size_t map_stride, float* map1_x, float* map1_y, float* map2_x, float* map2_y);
+
 /* Single-point helpers for cross-checks against cv2 / scipy. */
 /* aslam::PinholeCamera::project3 restated; returns 1 if the reference's keypoint_visible predicate
  * (ortho-backward-grid.cc:164-171) holds, 0 otherwise. */

@@ -75,6 +75,11 @@ def lib():
                                             C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                             C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ambo_stereo_reproject.restype = C.c_int
+        L.ambo_stereo_rectify_setup.argtypes = [C.c_void_p] * 9
+        L.ambo_stereo_rectify_setup.restype = C.c_int
+        L.ambo_stereo_rectify_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ambo_stereo_rectify_maps.restype = C.c_int
         L.ambo_project3.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p]
         L.ambo_project3.restype = C.c_int
         L.ambo_transform_to_camera.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]
@@ -234,6 +239,28 @@ def stereo_reproject(disparity, image_left, k4, baseline, R_G_C, t_G_C1, max_inv
     st = lib().ambo_stereo_reproject(_ptr(disp), w, _ptr(img), w, w, h, _ptr(k4), float(baseline), _ptr(R), _ptr(t),
                                      float(max_invalid_disparity), _ptr(xyz), _ptr(inten), h * w, C.byref(n))
     return st, xyz[:n.value].copy(), inten[:n.value].copy()
+
+
+def stereo_rectify_setup(K, R_G_C1, R_G_C2, t_G_C1, t_G_C2):
+    """Oracle Rectifier::rectifyStereoPair, host half.  Returns (status, baseline, R_G_C_rect, T1_inv, T2_inv)."""
+    a = [np.ascontiguousarray(m, dtype=np.float64).reshape(n) for m, n in
+         ((K, 9), (R_G_C1, 9), (R_G_C2, 9), (t_G_C1, 3), (t_G_C2, 3))]
+    base = np.zeros(1, np.float64)
+    R = np.zeros(9, np.float64)
+    T1, T2 = np.zeros(9, np.float32), np.zeros(9, np.float32)
+    st = lib().ambo_stereo_rectify_setup(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), _ptr(base),
+                                         _ptr(R), _ptr(T1), _ptr(T2))
+    return st, float(base[0]), R.reshape(3, 3), T1.reshape(3, 3), T2.reshape(3, 3)
+
+
+def stereo_rectify_maps(T1_inv, T2_inv, width, height):
+    """Oracle per-pixel map fill.  Returns (status, (map1_x, map1_y, map2_x, map2_y)) float32 [H, W]."""
+    T1 = np.ascontiguousarray(T1_inv, dtype=np.float32).reshape(9)
+    T2 = np.ascontiguousarray(T2_inv, dtype=np.float32).reshape(9)
+    maps = [np.empty((int(height), int(width)), np.float32) for _ in range(4)]
+    st = lib().ambo_stereo_rectify_maps(_ptr(T1), _ptr(T2), int(width), int(height), int(width), _ptr(maps[0]),
+                                        _ptr(maps[1]), _ptr(maps[2]), _ptr(maps[3]))
+    return st, tuple(maps)
 
 
 def ortho_process(geom, layers, camera, T_G_B, images, colored=False, num_threads=0, cell_range=None):
