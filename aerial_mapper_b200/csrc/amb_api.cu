@@ -308,12 +308,17 @@ int amb_ortho_from_pcl_process_device(amb_ctx* ctx, const double* d_xyz, const i
   if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
   if (n == 0) return AMB_ERR_EMPTY;  // CHECK(!pointcloud.empty()), ortho-from-pcl.cc:23
   if (!d_xyz || !d_intensities) return AMB_ERR_INVALID_ARGUMENT;
-  if (use_adaptive_interpolation) return AMB_ERR_UNSUPPORTED;  // unbounded 10^k radius growth: not on this path
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
   ctx->dsm_had_h2d = false;
+  float* saved = nullptr;  // adaptive interpolation (ortho-from-pcl.cc:63-72): pcl_adaptive_kernels.cu
+  if (use_adaptive_interpolation) {
+    const int pst = pcl_adaptive_prepare(ctx, &saved);
+    if (pst != AMB_OK) return pcl_adaptive_finish(ctx, pst, n, interpolation_radius, saved);
+  }
   int st = dsm_run(ctx, d_xyz, nullptr, n, interpolation_radius, 0.0, 0.0, 1, d_intensities);
+  if (use_adaptive_interpolation) st = pcl_adaptive_finish(ctx, st, n, interpolation_radius, saved);
   ctx->dsm_timed = (st == AMB_OK);
   return st;
 }
@@ -323,7 +328,6 @@ int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* i
   if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
   if (n == 0) return AMB_ERR_EMPTY;
   if (!xyz || !intensities) return AMB_ERR_INVALID_ARGUMENT;
-  if (use_adaptive_interpolation) return AMB_ERR_UNSUPPORTED;
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   AMB_CUDA(ctx, ctx->points.reserve(n * 3 * sizeof(double)));
   AMB_CUDA(ctx, ctx->intensities.reserve(n * sizeof(int32_t)));
@@ -333,8 +337,14 @@ int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* i
                                 ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
   ctx->dsm_had_h2d = true;
+  float* saved = nullptr;
+  if (use_adaptive_interpolation) {
+    const int pst = pcl_adaptive_prepare(ctx, &saved);
+    if (pst != AMB_OK) return pcl_adaptive_finish(ctx, pst, n, interpolation_radius, saved);
+  }
   int st = dsm_run(ctx, ctx->points.as<double>(), nullptr, n, interpolation_radius, 0.0, 0.0, 1,
                    ctx->intensities.as<int>());
+  if (use_adaptive_interpolation) st = pcl_adaptive_finish(ctx, st, n, interpolation_radius, saved);
   ctx->dsm_timed = (st == AMB_OK);
   if (st != AMB_OK) return st;
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -123,6 +123,7 @@ struct amb_ctx {
   bool dsm_debug = false;
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;
+  std::vector<unsigned char> last_dsm_plan;  // the DsmPlan of the last dsm_run (read by the adaptive OrthoFromPcl pass)
 
   // Ortho scratch
   amb::DeviceBuffer frames;       // device copies of the caller's frames (host entry point)
@@ -165,6 +166,9 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
 int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n, double y_lo,
                      double y_hi, double reach, double center_easting, double* d_out_xyz,
                      unsigned long long* d_out_ids, unsigned int capacity, unsigned int* d_count);
+// Implemented in pcl_adaptive_kernels.cu: ortho::Settings::use_adaptive_interpolation around dsm_run(mode = 1)
+int pcl_adaptive_prepare(amb_ctx* ctx, float** saved);
+int pcl_adaptive_finish(amb_ctx* ctx, int pass_status, size_t n, int32_t interpolation_radius, float* saved);
 int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
               const uint8_t* const* h_images, size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
 std::vector<double> dsm_thresholds(int32_t interpolation_radius);

@@ -958,6 +958,8 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   st = mirror_layer(ctx, out_layer);  // the result starts streaming to its host mirror (if one is registered)
   if (st != AMB_OK) return st;
   ctx->dsm_debug_valid = ctx->dsm_debug;
+  ctx->last_dsm_plan.assign(reinterpret_cast<const unsigned char*>(&plan),
+                            reinterpret_cast<const unsigned char*>(&plan) + sizeof(plan));
   return AMB_OK;
 }
 

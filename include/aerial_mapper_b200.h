@@ -199,8 +199,11 @@ int amb_dsm_thresholds(int32_t interpolation_radius, double* thresholds, int32_t
  * IDW of point INTENSITIES into the `ortho` layer: the DSM kernels with z = double(intensities[i]), one radius query
  * (ortho::Settings::interpolation_radius of ortho-from-pcl.h:28-35, default 2, squared metres), no centre shift, and
  * a zero-distance point taken as a "perfect match" (:90-96) instead of a CHECK failure.  Cells without a neighbour
- * keep their value.  use_adaptive_interpolation != 0 (the 10^k radius growth of :63-72, off in the demo's flag
- * file) returns AMB_ERR_UNSUPPORTED. */
+ * keep their value.  use_adaptive_interpolation != 0 (:63-72, off in the demo's flag file): a cell whose primary
+ * ball is empty takes the IDW over the first non-empty ball of the thresholds 10*r, 100*r, 1000*r, ... (`int`
+ * arithmetic in the reference, defined while 10^k * r <= INT_MAX), so every cell gets a value.  That mode needs a
+ * context owning the whole map and every point inside the map's bin grid (map + the apron of the search radius);
+ * otherwise AMB_ERR_UNSUPPORTED and the layer keeps its content. */
 int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* intensities, size_t n,
                                int32_t interpolation_radius, int32_t use_adaptive_interpolation);
 int amb_ortho_from_pcl_process_device(amb_ctx* ctx, const double* d_xyz, const int32_t* d_intensities, size_t n,
