@@ -12,6 +12,8 @@
  *     they lie, against stand-in headers for the absent third-party libraries (refsrc_stubs/amb_refsrc_deps.h lists
  *     exactly what is reference code and what is restated).  tests/test_oracle_refsrc.py: the restated loops are
  *     bit-identical to the reference's own code on every layer; the committed golden fixtures likewise.
+ *   - oracle/_ref/libamb_refsrc_stereo.so: the reference's densifier.cpp likewise ("next" row N3); stereo_oracle.cc is
+ *     bit-identical to it (tests/test_stereo_reproject.py).
  *   - oracle/_ref/libamb_oracle_ref.so: nanoflann.hpp verbatim around the restated cell loop (exposes neighbour
  *     counts / retry levels); the dependency-free restatement in dsm_oracle.cc is checked against it.
  *   - brute force / scipy.spatial.cKDTree for neighbour sets, cv2.projectPoints for the camera model, scipy Rotation

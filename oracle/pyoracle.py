@@ -20,6 +20,7 @@ _REF_PATH = os.path.join(_HERE, "_ref", "libamb_oracle_ref.so")
 _REFSRC_MAIN_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_main.so")
 _REFSRC_PCL_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_pcl.so")
 _REFERENCE_DEMO_PATH = os.path.join(_HERE, "_ref", "libamb_reference_demo.so")
+_REFSRC_STEREO_PATH = os.path.join(_HERE, "_ref", "libamb_refsrc_stereo.so")
 _REFERENCE_ROOT = "/root/reference"
 
 
@@ -147,6 +148,34 @@ def refsrc():
         P.ambo_refsrc_pcl_last_error.restype = C.c_char_p
         _refsrc = (M, P)
     return _refsrc
+
+
+def have_refsrc_stereo():
+    if os.path.isdir(_REFERENCE_ROOT):
+        build()
+    return os.path.exists(_REFSRC_STEREO_PATH)
+
+
+def refsrc_stereo_reproject(disparity, image_left, k4, baseline, R_G_C, t_G_C1):
+    """stereo::Densifier::computePointCloud — the reference's densifier.cpp compiled verbatim (oracle/_ref).
+    Returns (status, xyz [n,3] float64, intensities [n] int32); kMaxInvalidDisparity is the reference's constant 1."""
+    L = C.CDLL(_REFSRC_STEREO_PATH)
+    L.ambo_refsrc_stereo_reproject.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32,
+                                               C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.POINTER(C.c_size_t)]
+    L.ambo_refsrc_stereo_reproject.restype = C.c_int
+    disp = np.ascontiguousarray(disparity, dtype=np.float32)
+    img = np.ascontiguousarray(image_left, dtype=np.uint8)
+    h, w = disp.shape
+    k4 = np.ascontiguousarray(k4, dtype=np.float64)
+    R = np.ascontiguousarray(R_G_C, dtype=np.float64).reshape(9)
+    t = np.ascontiguousarray(t_G_C1, dtype=np.float64).reshape(3)
+    xyz = np.empty((h * w, 3), np.float64)
+    inten = np.empty(h * w, np.int32)
+    n = C.c_size_t(0)
+    st = L.ambo_refsrc_stereo_reproject(_ptr(disp), w, _ptr(img), w, w, h, _ptr(k4), float(baseline), _ptr(R), _ptr(t),
+                                        _ptr(xyz), _ptr(inten), h * w, C.byref(n))
+    return st, xyz[:n.value].copy(), inten[:n.value].copy()
 
 
 def have_reference_demo():

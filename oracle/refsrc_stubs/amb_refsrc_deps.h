@@ -441,6 +441,13 @@ class NCamera {
 /* ------------------------------------------------------------------ OpenCV ---------------------------------- */
 typedef unsigned char uchar;
 namespace cv {
+struct Size {
+  int width, height;
+  Size() : width(0), height(0) {}
+  Size(int w, int h) : width(w), height(h) {}
+  bool operator==(const Size& o) const { return width == o.width && height == o.height; }
+  bool operator!=(const Size& o) const { return !(*this == o); }
+};
 struct Vec3b {
   uchar val[3];
   const uchar& operator[](int i) const { return val[i]; }
@@ -462,6 +469,15 @@ class Mat {
   const T& at(int row, int col) const {
     return *reinterpret_cast<const T*>(data + static_cast<size_t>(row) * step + static_cast<size_t>(col) * sizeof(T));
   }
+  template <typename T>
+  T* ptr(int row) {
+    return reinterpret_cast<T*>(data + static_cast<size_t>(row) * step);
+  }
+  template <typename T>
+  const T* ptr(int row) const {
+    return reinterpret_cast<const T*>(data + static_cast<size_t>(row) * step);
+  }
+  Size size() const { return Size(cols, rows); }
   bool empty() const { return data == nullptr; }
   int channels() const { return channels_; }
   int rows, cols;

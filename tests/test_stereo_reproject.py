@@ -48,6 +48,30 @@ def test_oracle_matches_numpy():
     assert po.stereo_reproject(disp, img, k4, 0.0, Rm, t)[0] == -6    # CHECK_NE(baseline, 0.0)
 
 
+@pytest.mark.parametrize("h,w,seed", [(37, 53, 1), (240, 376, 6), (1, 7, 4), (64, 300, 7)])
+def test_oracle_equals_the_reference_densifier_cpp(h, w, seed):
+    # oracle/_ref/libamb_refsrc_stereo.so: the reference's own densifier.cpp compiled verbatim against stand-in
+    # third-party headers (oracle/refsrc_stubs/amb_refsrc_stereo_deps.h): same points, same order, same bits
+    if not po.have_refsrc_stereo():
+        pytest.skip("oracle/_ref/libamb_refsrc_stereo.so not built (needs /root/reference)")
+    disp, img, k4, b, Rm, t = scenario(h, w, seed)
+    disp[0, :3] = (np.float32(1.0), np.nextafter(np.float32(1.0), np.float32(2.0)), np.float32(0.0))
+    st, xyz, inten = po.stereo_reproject(disp, img, k4, b, Rm, t)
+    st2, rxyz, rinten = po.refsrc_stereo_reproject(disp, img, k4, b, Rm, t)
+    assert st == 0 and st2 == 0 and xyz.shape == rxyz.shape and len(xyz) > 0
+    assert np.array_equal(xyz.view(np.uint64), rxyz.view(np.uint64))
+    assert np.array_equal(inten, rinten)
+    # an (almost) infinite depth: the float copy of z overflows -> the reference drops the point (:78)
+    d2 = np.full((2, 3), 2.0, np.float32)
+    d2[0, 0] = np.float32(1e-38)                      # valid only if > kMaxInvalidDisparity: it is not
+    d2[1, 1] = np.float32(1.0000001)
+    i2 = np.arange(6, dtype=np.uint8).reshape(2, 3)
+    a = po.stereo_reproject(d2, i2, k4, b, Rm * 1e37, t)
+    r = po.refsrc_stereo_reproject(d2, i2, k4, b, Rm * 1e37, t)
+    assert a[0] == 0 and r[0] == 0 and np.array_equal(a[1].view(np.uint64), r[1].view(np.uint64))
+    assert np.array_equal(a[2], r[2]) and len(a[2]) < 5   # z overflowed float32 for the kept disparities
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("h,w,seed", [(37, 53, 2), (480, 752, 3), (1, 7, 4), (300, 1000, 5)])
 def test_gpu_matches_oracle_bit_for_bit(h, w, seed):
