@@ -97,6 +97,7 @@ SYMBOLS = {
     "amb_ortho_process_device": (C.c_int, [_P, C.POINTER(Camera), _P, _P, C.c_size_t, C.c_int32, C.c_size_t,
                                            C.c_int32]),
     "amb_ortho_set_brute_force": (C.c_int, [_P, C.c_int]),
+    "amb_ortho_set_dominance_cull": (C.c_int, [_P, C.c_int]),
     "amb_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "amb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "amb_host_free": (C.c_int, [_P]),

@@ -13,6 +13,7 @@ The C++ drop-in headers with the literal reference signatures live in aerial_map
 All compute happens in libaerial_mapper_b200.so on the GPU; there is no CPU path in this package.
 """
 import ctypes as C
+import os
 import logging
 
 import numpy as np
@@ -351,6 +352,9 @@ class OrthoBackwardGrid(object):
         self.ncameras_ = ncameras
         self.settings_ = settings
         self.brute_force = False
+        # opt-in per-tile dominance cull of the frame list (amb_ortho_set_dominance_cull); AMB_ORTHO_DOMINANCE=1 turns
+        # it on for every instance (how the pending GPU tests and the bench exercise it before it becomes the default)
+        self.dominance_cull = os.environ.get("AMB_ORTHO_DOMINANCE", "0") not in ("", "0")
 
     def _layers_written(self):
         out = "colored_ortho" if self.settings_.colored_ortho else "ortho"
@@ -384,6 +388,7 @@ class OrthoBackwardGrid(object):
         if not map.is_resident():
             map.upload(("elevation",) + self._layers_written())
         check(lib().amb_ortho_set_brute_force(ctx, 1 if self.brute_force else 0), ctx)
+        check(lib().amb_ortho_set_dominance_cull(ctx, 1 if self.dominance_cull else 0), ctx)
         check(lib().amb_ortho_process(ctx, C.byref(cam), T.ctypes.data_as(C.c_void_p), C.cast(ptrs, C.c_void_p), n,
                                       channels, row_step, 1 if colored else 0), ctx)
         if not map.is_resident():
@@ -399,6 +404,7 @@ class OrthoBackwardGrid(object):
         ptrs = (C.c_void_p * n)(*[int(p) for p in d_image_ptrs])
         ctx = map.context()
         check(lib().amb_ortho_set_brute_force(ctx, 1 if self.brute_force else 0), ctx)
+        check(lib().amb_ortho_set_dominance_cull(ctx, 1 if self.dominance_cull else 0), ctx)
         check(lib().amb_ortho_process_device(ctx, C.byref(self.ncameras_.camera), T.ctypes.data_as(C.c_void_p),
                                              C.cast(ptrs, C.c_void_p), n, 3 if colored else 1, int(row_step),
                                              1 if colored else 0), ctx)

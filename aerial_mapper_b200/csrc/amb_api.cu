@@ -472,6 +472,12 @@ int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force) {
   return AMB_OK;
 }
 
+int amb_ortho_set_dominance_cull(amb_ctx* ctx, int enable) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->ortho_dominance = enable != 0;
+  return AMB_OK;
+}
+
 // ---- measurement ----
 int amb_get_timings(amb_ctx* ctx, amb_timings* out) {
   if (!ctx || !out) return AMB_ERR_INVALID_ARGUMENT;

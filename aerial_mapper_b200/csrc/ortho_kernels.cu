@@ -69,6 +69,11 @@ struct OrthoArgs {
   double fu, fv, cu, cv;
   double d0, d1, d2, d3;
   double cos_c, sin_c;            // half-angle of the conservative view cone
+  // --- dominance cull (DOM instances only; appended so that every earlier field keeps its offset) ---
+  // every ray with undistorted normalised keypoint inside [ui_lo, ui_hi] x [vi_lo, vi_hi] (and z_c > 0) IS visible
+  double ui_lo, ui_hi, vi_lo, vi_hi;
+  double nui_lo, nui_hi, nvi_lo, nvi_hi;  // sqrt(1 + bound^2)
+  double dom_margin;                      // rad
 };
 
 // Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed + one cubic correction step.
@@ -133,265 +138,16 @@ __device__ __forceinline__ double observation_angle(double xc, double yc, double
 // SELECT = true:  phase A of the host-frame path: no texel access at all; records the winner's pixel per cell and
 //                 the bounding box of the winners' pixels per frame, so that only those sub-rectangles of the
 //                 host frames have to cross PCIe (phase B: ortho_texel_kernel).
-template <int DIST, bool SELECT>
-__global__ void __launch_bounds__(kOrthoThreads, 3) ortho_kernel(const __grid_constant__ OrthoArgs a) {
-  __shared__ unsigned short s_list[kMaxFramesPerLaunch];
-  __shared__ int s_bbox[SELECT ? 4 * kMaxFramesPerLaunch : 4];
-  __shared__ float s_red[2][kOrthoThreads / 32];
-  __shared__ int s_warp_cnt[kOrthoThreads / 32];
-  __shared__ int s_total;
-
-  const int ti = threadIdx.x & 31, tq = threadIdx.x >> 5;
-  const int tiles_i = (a.rows + OTI - 1) / OTI;
-  const int i0 = (blockIdx.x % tiles_i) * OTI;
-  const int j0 = (blockIdx.x / tiles_i) * OTJ;
-  const int i = i0 + ti;
-  const int jl0 = j0 + kOStrip * tq;
-
-  float elev[kOStrip];
-  unsigned int validmask = 0;
-  float zmin = FLT_MAX, zmax = -FLT_MAX;
-#pragma unroll
-  for (int m = 0; m < kOStrip; ++m) {
-    elev[m] = __int_as_float(0x7fc00000);
-    if (i < a.rows && jl0 + m < a.cols_slab) elev[m] = a.elevation[static_cast<size_t>(jl0 + m) * a.rows + i];
-    if (!isnan(elev[m])) {  // NaN elevation: every comparison is false, the cell stays untouched
-      validmask |= 1u << m;
-      zmin = fminf(zmin, elev[m]);
-      zmax = fmaxf(zmax, elev[m]);
-    }
-  }
-  // tile elevation range
-  for (int o = 16; o > 0; o >>= 1) {
-    zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
-    zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-  }
-  if (ti == 0) {
-    s_red[0][tq] = zmin;
-    s_red[1][tq] = zmax;
-  }
-  if (threadIdx.x == 0) s_total = 0;
-  if (SELECT) {
-    for (int e = threadIdx.x; e < 2 * kMaxFramesPerLaunch; e += kOrthoThreads) {
-      s_bbox[e] = 0x7fffffff;                            // xmin, ymin
-      s_bbox[2 * kMaxFramesPerLaunch + e] = -1;          // xmax, ymax
-    }
-  }
-  __syncthreads();
-  zmin = s_red[0][0];
-  zmax = s_red[1][0];
-#pragma unroll
-  for (int w = 1; w < kOrthoThreads / 32; ++w) {
-    zmin = fminf(zmin, s_red[0][w]);
-    zmax = fmaxf(zmax, s_red[1][w]);
-  }
-  if (zmin > zmax) return;  // no cell of this tile has an elevation
-
-  // bounding sphere of the tile's landmarks (cell centres x elevation range)
-  const int i1 = min(i0 + OTI, a.rows) - 1, j1 = min(j0 + OTJ, a.cols_slab) - 1;
-  const double x_hi = a.base_x - a.res * i0, x_lo = a.base_x - a.res * i1;
-  const double y_hi = a.base_y - a.res * (a.col_begin + j0), y_lo = a.base_y - a.res * (a.col_begin + j1);
-  const double sx = 0.5 * (x_hi + x_lo), sy = 0.5 * (y_hi + y_lo);
-  const double sz = 0.5 * (static_cast<double>(zmin) + static_cast<double>(zmax));
-  const double ex = 0.5 * (x_hi - x_lo), ey = 0.5 * (y_hi - y_lo);
-  const double ez = 0.5 * (static_cast<double>(zmax) - static_cast<double>(zmin));
-  const double rho = sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9) + 1e-6;
-
-  // ordered list of the frames that may see the tile
-  for (int f0 = 0; f0 < a.n_frames; f0 += kOrthoThreads) {
-    const int f = f0 + threadIdx.x;
-    bool keep = f < a.n_frames;
-    if (keep && a.do_cull) {
-      // per-thread frame index: read from global memory (a divergent __constant__ index would serialise)
-      const double* cf = a.cull_data + 12 * static_cast<size_t>(f);
-      const double dx = sx - __ldg(cf + 0), dy = sy - __ldg(cf + 1), dz = sz - __ldg(cf + 2);
-      const double xp = dx * __ldg(cf + 3) + dy * __ldg(cf + 4) + dz * __ldg(cf + 5);    // x_c of the centre
-      const double yp = dx * __ldg(cf + 6) + dy * __ldg(cf + 7) + dz * __ldg(cf + 8);    // y_c
-      const double zp = dx * __ldg(cf + 9) + dy * __ldg(cf + 10) + dz * __ldg(cf + 11);  // z_c (optical axis)
-      const double dd = dx * dx + dy * dy + dz * dz;
-      const double slack = rho + 1e-9 * (fabs(xp) + fabs(yp) + fabs(zp));
-      if (zp + rho <= 0.0) {
-        keep = false;  // whole sphere behind the camera plane: z_c <= 0 for every landmark
-      } else {
-        if (a.cone) {
-          const double perp = sqrt(fmax(dd - zp * zp, 0.0));
-          // distance from the sphere centre to the solid cone {angle to axis <= theta_c} is at least
-          // perp*cos(theta_c) - zp*sin(theta_c)
-          if (perp * a.cos_c - zp * a.sin_c > slack) keep = false;
-        }
-        if (a.rect) {
-          // a landmark with z_c > 0 and u = x_c/z_c > u_hi has x_c - u_hi*z_c > 0: the sphere lies entirely on
-          // that side of the plane through the camera centre iff the centre's value exceeds rho*|normal|
-          if (xp - a.u_hi * zp > slack * a.nu_hi) keep = false;
-          if (a.u_lo * zp - xp > slack * a.nu_lo) keep = false;
-          if (yp - a.v_hi * zp > slack * a.nv_hi) keep = false;
-          if (a.v_lo * zp - yp > slack * a.nv_lo) keep = false;
-        }
-      }
-    }
-    const unsigned int mk = __ballot_sync(0xffffffffu, keep);
-    if (ti == 0) s_warp_cnt[tq] = __popc(mk);
-    __syncthreads();
-    int before = s_total;
-    for (int w = 0; w < tq; ++w) before += s_warp_cnt[w];
-    if (keep) s_list[before + __popc(mk & ((1u << ti) - 1u))] = static_cast<unsigned short>(f);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = s_total;
-      for (int w = 0; w < kOrthoThreads / 32; ++w) t += s_warp_cnt[w];
-      s_total = t;
-    }
-    __syncthreads();
-  }
-  const int n_list = s_total;
-  if (n_list == 0) return;
-  if (!SELECT && !validmask) return;  // (SELECT: every thread reaches the block-wide bbox flush below)
-
-  // ---- winner selection: the reference's recurrence  `alpha_f > (double)best_f32  =>  best_f32 = (float)alpha_f`
-  // with alpha = asin(|z|/norm)  (ortho-backward-grid.cc:173-183), evaluated WITHOUT an asin per candidate.
-  // asin is increasing with slope >= 1, so comparing s2 = z^2/norm^2 = sin^2(alpha) decides the comparison
-  // whenever the gap is larger than what the float32 rounding of the running best can hide:
-  //   running best known exactly (layer value b):          ref2 = sin^2(b), band 1e-11
-  //   running best = (float)asin(s_p) of a pending winner: ref2 = s_p^2,    band 2e-7
-  //       (|(float)a - a| <= 6.0e-8 * a <= 9.4e-8;  s2_f - s2_p > 2e-7  =>  s_f - s_p > 1e-7  =>  alpha_f - alpha_p > 1e-7)
-  // Inside the band the decision is made exactly as the reference does (asin of both, float-rounded best).
-  const double X = __dadd_rn(a.base_x, __dmul_rn(a.res, -static_cast<double>(i)));
-  double Y[kOStrip], Z[kOStrip], thr_hi[kOStrip], thr_lo[kOStrip];
-  float best[kOStrip];
-  int best_f[kOStrip];
-  unsigned int pending = 0;  // bit m: best_f[m] won but (float)asin(...) has not been evaluated yet
-#pragma unroll
-  for (int m = 0; m < kOStrip; ++m) {
-    Y[m] = __dadd_rn(a.base_y, __dmul_rn(a.res, -static_cast<double>(a.col_begin + jl0 + m)));
-    Z[m] = static_cast<double>(elev[m]);
-    best[m] = 0.0f;
-    best_f[m] = -1;
-    double ref2 = 4.0, band = 0.0;  // invalid cell: nothing can win
-    if ((validmask >> m) & 1u) {
-      best[m] = a.elevation_angle[static_cast<size_t>(jl0 + m) * a.rows + i];
-      if (best[m] > 0.0f) {
-        const double sb = sin(static_cast<double>(best[m]));
-        ref2 = sb * sb;
-        band = 1e-11;
-      } else if (best[m] == 0.0f) {
-        ref2 = 0.0;  // any visible frame has alpha > 0
-      } else if (best[m] < 0.0f) {
-        ref2 = -1.0;  // a negative layer value is beaten by anything; NaN (ref2 = 4) by nothing
-      }
-    }
-    thr_hi[m] = ref2 + band;
-    thr_lo[m] = ref2 - band;
-  }
-  bool check_failed = false;
-  unsigned int dirty = 0;  // bit m: a candidate fell inside the band -> redo that cell exactly after the loop
-
-  // Hot loop: straight-line code, four independent dependency chains per thread (one per cell of the strip).
-  for (int l = 0; l < n_list; ++l) {
-    const int f = s_list[l];
-    const FrameConst& fc = c_frames[f];
-    const double cx = fma(fc.m[0], X, fc.t[0]);
-    const double cy = fma(fc.m[3], X, fc.t[1]);
-    const double cz = fma(fc.m[6], X, fc.t[2]);
-#pragma unroll
-    for (int m = 0; m < kOStrip; ++m) {
-      const double xc = fma(fc.m[1], Y[m], fma(fc.m[2], Z[m], cx));
-      const double yc = fma(fc.m[4], Y[m], fma(fc.m[5], Z[m], cy));
-      const double zc = fma(fc.m[7], Y[m], fma(fc.m[8], Z[m], cz));
-      double kx, ky;
-      const bool vis = project<DIST>(a, xc, yc, zc, &kx, &ky);
-      const double z2 = zc * zc;
-      const double n2 = fma(xc, xc, fma(yc, yc, z2));
-      const bool win = vis && (z2 > thr_hi[m] * n2);
-      const bool unc = vis && !win && (z2 >= thr_lo[m] * n2);
-      dirty |= (unc ? 1u : 0u) << m;
-      const double ref2 = z2 * fast_rcp(n2);
-      best_f[m] = win ? f : best_f[m];
-      thr_hi[m] = win ? ref2 + 2e-7 : thr_hi[m];
-      thr_lo[m] = win ? ref2 - 2e-7 : thr_lo[m];
-      pending |= (win ? 1u : 0u) << m;
-    }
-  }
-
-  if (dirty) {
-    // Rare (a near-tie within the float32 rounding of the running best): evaluate the reference's recurrence
-    // literally for those cells — asin for every visible frame, float-rounded best (:173-183).
-#pragma unroll
-    for (int m = 0; m < kOStrip; ++m) {  // unrolled: the per-cell arrays must stay in registers
-      if (!((dirty >> m) & 1u)) continue;
-      float b = a.elevation_angle[static_cast<size_t>(jl0 + m) * a.rows + i];
-      int bf = -1;
-      for (int l = 0; l < n_list; ++l) {
-        const int f = s_list[l];
-        double xc, yc, zc, kx, ky;
-        to_camera(f, X, Y[m], Z[m], &xc, &yc, &zc);
-        if (!project<DIST>(a, xc, yc, zc, &kx, &ky)) continue;
-        const double alpha = observation_angle(xc, yc, zc);
-        if (!(alpha > 0.0)) check_failed = true;  // reference: CHECK(alpha > 0.0), :178
-        if (alpha > static_cast<double>(b)) {     // :180
-          b = static_cast<float>(alpha);          // :181
-          bf = f;
-        }
-      }
-      best[m] = b;
-      best_f[m] = bf;
-      pending &= ~(1u << m);
-    }
-  }
-
-#pragma unroll
-  for (int m = 0; m < kOStrip; ++m) {
-    if (best_f[m] < 0) continue;
-    const size_t cell = static_cast<size_t>(jl0 + m) * a.rows + i;
-    // the winner's camera coordinates and keypoint, recomputed (the reference projects a second time too, :186-188)
-    double xc, yc, zc, kx, ky;
-    to_camera(best_f[m], X, Y[m], Z[m], &xc, &yc, &zc);
-    project<DIST>(a, xc, yc, zc, &kx, &ky);
-    if ((pending >> m) & 1u) {
-      const double alpha = observation_angle(xc, yc, zc);
-      if (!(alpha > 0.0)) check_failed = true;
-      best[m] = static_cast<float>(alpha);
-    }
-    a.elevation_angle[cell] = best[m];
-    a.observation_index[cell] = static_cast<float>(a.frame_base + best_f[m]);  // :182
-    // :183 num_observations += num_observations — 0 stays 0, layer untouched.
-    // :186-193 — round half away from zero, clamp to the last row / column.
-    const int py = min(static_cast<int>(round(ky)), a.height - 1);
-    const int px = min(static_cast<int>(round(kx)), a.width - 1);
-    if (SELECT) {
-      a.pix[cell] = (static_cast<unsigned int>(py) << 16) | static_cast<unsigned int>(px);
-      const int bf = best_f[m];
-      atomicMin(&s_bbox[bf], px);
-      atomicMin(&s_bbox[kMaxFramesPerLaunch + bf], py);
-      atomicMax(&s_bbox[2 * kMaxFramesPerLaunch + bf], px);
-      atomicMax(&s_bbox[3 * kMaxFramesPerLaunch + bf], py);
-    } else {
-      const uint8_t* img = a.images[best_f[m]];
-      const uint8_t* texel = img + static_cast<size_t>(py) * a.row_step + static_cast<size_t>(px) * a.channels;
-      if (a.colored) {
-        // :194-202 + grid_map::colorVectorToValue: cv::Vec3b is (B,G,R); the packed value is 0x00RRGGBB moved as
-        // raw bits (int(float(c/255.0)*255.0f) == c for every byte c; tests/test_oracle_ortho.py checks all 256).
-        const unsigned int b = __ldg(texel), g = __ldg(texel + 1), r = __ldg(texel + 2);
-        a.out_layer[cell] = __uint_as_float((r << 16) | (g << 8) | b);
-      } else {
-        a.out_layer[cell] = static_cast<float>(__ldg(texel));  // :203-206
-      }
-    }
-  }
-  if (check_failed) atomicExch(a.error_flag, 1u);
-  if (SELECT) {
-    __syncthreads();
-    for (int l = threadIdx.x; l < n_list; l += kOrthoThreads) {
-      const int f = s_list[l];
-      if (s_bbox[2 * kMaxFramesPerLaunch + f] >= 0) {
-        int* g = a.bbox + 4 * (a.frame_base + f);
-        atomicMin(g + 0, s_bbox[f]);
-        atomicMin(g + 1, s_bbox[kMaxFramesPerLaunch + f]);
-        atomicMax(g + 2, s_bbox[2 * kMaxFramesPerLaunch + f]);
-        atomicMax(g + 3, s_bbox[3 * kMaxFramesPerLaunch + f]);
-      }
-    }
-  }
-}
+#define AMB_ORTHO_DOM 0
+#define AMB_ORTHO_KERNEL_NAME ortho_kernel
+#include "ortho_kernel_body.inc"
+#undef AMB_ORTHO_DOM
+#undef AMB_ORTHO_KERNEL_NAME
+#define AMB_ORTHO_DOM 1
+#define AMB_ORTHO_KERNEL_NAME ortho_kernel_dom
+#include "ortho_kernel_body.inc"
+#undef AMB_ORTHO_DOM
+#undef AMB_ORTHO_KERNEL_NAME
 
 // Bounding boxes device -> HOST-MAPPED pinned memory with plain stores: the read-back must not queue behind the
 // result layers that are streaming to the host on the device->host copy engine.
@@ -688,6 +444,28 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.nv_hi = std::sqrt(1.0 + a.v_hi * a.v_hi);
   }
 
+  // Dominance cull (opt-in, amb_ortho_set_dominance_cull): needs the view rectangle (pinhole / rad-tan) and a
+  // non-empty INNER rectangle — the raster's normalised extent shrunk by the same distortion bound E the outer
+  // rectangle was grown by: a ray with an undistorted keypoint inside it is imaged inside the raster.
+  bool dominance = false;
+  if (ctx->ortho_dominance && a.do_cull && a.rect && a.dist_type != AMB_DIST_EQUIDISTANT) {
+    const double E_u = a.u_hi - (camera->width - camera->cu) / camera->fu;   // what compute_view_rect added
+    const double E_v = a.v_hi - (camera->height - camera->cv) / camera->fv;
+    const double E = std::max(E_u, E_v) * (1.0 + 1e-9) + 1e-9;
+    a.ui_lo = -camera->cu / camera->fu + E;
+    a.ui_hi = (camera->width - camera->cu) / camera->fu - E;
+    a.vi_lo = -camera->cv / camera->fv + E;
+    a.vi_hi = (camera->height - camera->cv) / camera->fv - E;
+    if (a.ui_lo < a.ui_hi && a.vi_lo < a.vi_hi) {
+      a.nui_lo = std::sqrt(1.0 + a.ui_lo * a.ui_lo);
+      a.nui_hi = std::sqrt(1.0 + a.ui_hi * a.ui_hi);
+      a.nvi_lo = std::sqrt(1.0 + a.vi_lo * a.vi_lo);
+      a.nvi_hi = std::sqrt(1.0 + a.vi_hi * a.vi_hi);
+      a.dom_margin = 1e-4;  // rad; the float32 rounding of an angle <= pi/2 is < 1.2e-7
+      dominance = true;
+    }
+  }
+
   const int tiles_i = (a.rows + OTI - 1) / OTI, tiles_j = (a.cols_slab + OTJ - 1) / OTJ;
   ctx->ortho_launches = 0;
   for (size_t f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {  // ascending chunks keep the frame order
@@ -703,7 +481,19 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.images = ctx->frame_table.as<const uint8_t*>() + f0;
     a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
     const int grid = tiles_i * tiles_j;
-    if (select_only) {
+    if (dominance) {  // pinhole / rad-tan only (see above)
+      if (select_only) {
+        if (a.dist_type == AMB_DIST_RADTAN) {
+          ortho_kernel_dom<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
+        } else {
+          ortho_kernel_dom<AMB_DIST_NONE, true><<<grid, kOrthoThreads, 0, s>>>(a);
+        }
+      } else if (a.dist_type == AMB_DIST_RADTAN) {
+        ortho_kernel_dom<AMB_DIST_RADTAN, false><<<grid, kOrthoThreads, 0, s>>>(a);
+      } else {
+        ortho_kernel_dom<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
+      }
+    } else if (select_only) {
       if (a.dist_type == AMB_DIST_RADTAN) {
         ortho_kernel<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
       } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {

@@ -362,7 +362,8 @@ def run_ours(args):
                       "frames": "%dx %dx%d gray" % (n_frames, W, H), "interpolation_radius": 1,
                       "sharding": ("column stripes x%d; cloud sharded by stripe; 1 all-gather of border halos/step; layers "
                                    "stay sharded" % world) if world > 1 else "single GPU",
-                      "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W) / 1e9)},
+                      "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W) / 1e9),
+                      "ortho_dominance_cull": bool(ortho.dominance_cull)},   # opt-in (AMB_ORTHO_DOMINANCE=1)
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if e2e is not None:
         out["e2e"] = e2e
