@@ -64,12 +64,26 @@ static_assert(TJ == kStrip * (kGatherThreads / 32), "one warp per strip row of t
 
 // One 32-byte record = one 256-bit access (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256) = exactly one DRAM sector.
 __device__ __forceinline__ void store_rec(PointRec* dst, double x, double y, double z, unsigned long long idx) {
+#ifdef AMB_CUDA_EMU  // tests/emu (CPU emulation of the kernel source)
+  dst->x = x;
+  dst->y = y;
+  dst->z = z;
+  dst->idx = idx;
+#else
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(z),
                "d"(__longlong_as_double(static_cast<long long>(idx)))
                : "memory");
+#endif
 }
 __device__ __forceinline__ void load_rec(const PointRec* src, double* x, double* y, double* z, double* idx_bits) {
+#ifdef AMB_CUDA_EMU
+  *x = src->x;
+  *y = src->y;
+  *z = src->z;
+  *idx_bits = __longlong_as_double(static_cast<long long>(src->idx));
+#else
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(*x), "=d"(*y), "=d"(*z), "=d"(*idx_bits) : "l"(src));
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -62,7 +62,11 @@ __device__ __forceinline__ bool fine_bin(const DsmPlan& p, double px, double py,
 // and one FMA; the IDW height changes by O(1e-16) relative, far inside the float32 layer's rounding.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
+#ifdef AMB_CUDA_EMU  // tests/emu (CPU emulation of the kernel source): no MUFU — an exact seed, same correction
+  r = 1.0 / x;
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   const double e = fma(-x, r, 1.0);  // |e| <= 2^-20
   const double t = fma(e, e, e);     // e + e^2: r*(1 + e + e^2) leaves a relative error e^3 <= 2^-60
   return fma(r, t, r);

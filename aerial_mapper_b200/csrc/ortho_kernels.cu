@@ -79,7 +79,11 @@ struct OrthoArgs {
 // Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed + one cubic correction step.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
+#ifdef AMB_CUDA_EMU  // tests/emu (CPU emulation of the kernel source): no MUFU — an exact seed, same correction
+  r = 1.0 / x;
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   const double e = fma(-x, r, 1.0);
   const double t = fma(e, e, e);
   return fma(r, t, r);

@@ -15,6 +15,30 @@ def pytest_configure(config):
                             "then promote to `gpu`")
 
 
+EMULATED = os.environ.get("AMB_TEST_EMU", "0") not in ("", "0")
+
+
+def _swap_in_the_emulated_library():
+    """AMB_TEST_EMU=1 (set only by tests/test_emulated_kernels.py for a child pytest process): the tests of this process
+    talk to tests/emu/_build/libamb_emu.so — the product's CUDA SOURCES compiled as plain C++ on a CPU stand-in for
+    the CUDA runtime (tests/emu/README.md) — so that kernel logic, incl. kernels that have not yet run on a GPU, is
+    exercised on a box without one.  The product package itself never does this."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from aerial_mapper_b200 import _lib
+    L = ctypes.CDLL(build_emu.build())
+    for name, (restype, argtypes) in _lib.SYMBOLS.items():
+        fn = getattr(L, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib._lib = L
+
+
+if EMULATED:
+    _swap_in_the_emulated_library()
+
+
 def _gpu_count():
     try:
         import aerial_mapper_b200 as amb
