@@ -43,16 +43,44 @@ def test_dominance_cull_changes_nothing(monkeypatch, colored, dist_type):
     assert_parity(gm, oracle_ortho(rows, cols, res, elev, camd, poses, imgs, colored), colored)
 
 
+def frames_per_tile(key):
+    """tests/emu only: mean length of the tiles' frame lists since the last call (None on the real library)."""
+    import ctypes as C
+    L = amb.lib()
+    if not hasattr(L, "amb_emu_counter"):
+        return None
+    s, n = C.c_longlong(), C.c_longlong()
+    L.amb_emu_counter(key, C.byref(s), C.byref(n))
+    return s.value / max(1, n.value)
+
+
 def test_wide_map_many_frames_where_the_cull_bites(monkeypatch):
     # footprints much smaller than the map, 60 frames: most tiles keep 1-3 of ~10 candidates
     rows, cols, res = 960, 640, 0.5
     camd, poses, imgs = make_inputs(rows, cols, res, 6, 10, 60.0, 0.1, False)
     elev = synth.analytic_elevation(rows, cols, res)
+    frames_per_tile(b"ortho_list"), frames_per_tile(b"ortho_dom_list")
     gm = both(monkeypatch, rows, cols, res, elev, camd, poses, imgs, False)
+    plain_n, dom_n = frames_per_tile(b"ortho_list"), frames_per_tile(b"ortho_dom_list")
+    if plain_n is not None:                  # emulated kernels: the dominance variant really ran, and it culled
+        assert 0 < dom_n < plain_n
     assert_parity(gm, oracle_ortho(rows, cols, res, elev, camd, poses, imgs, False), False)
     monkeypatch.setenv("AMB_ORTHO_DOMINANCE", "1")
     brute = gpu_ortho(rows, cols, res, elev, camd, poses, imgs, False, brute=True)   # brute force ignores the cull
     assert np.array_equal(gm["observation_index"], brute["observation_index"], equal_nan=True)
+
+
+def test_benchmark_like_geometry_keeps_one_or_two_frames_per_tile(monkeypatch):
+    # flight height >> tile size, every frame sees every tile (like joint_10k): 30 candidates -> ~2 survivors per tile
+    rows, cols, res = 640, 640, 0.25
+    camd, poses, imgs = make_inputs(rows, cols, res, 5, 6, 400.0, 0.1, False)
+    elev = synth.analytic_elevation(rows, cols, res)
+    frames_per_tile(b"ortho_list"), frames_per_tile(b"ortho_dom_list")
+    gm = both(monkeypatch, rows, cols, res, elev, camd, poses, imgs, False)
+    assert_parity(gm, oracle_ortho(rows, cols, res, elev, camd, poses, imgs, False), False)
+    plain_n, dom_n = frames_per_tile(b"ortho_list"), frames_per_tile(b"ortho_dom_list")
+    if plain_n is not None:
+        assert plain_n > 25 and dom_n < 4
 
 
 def test_rough_terrain_and_tilted_cameras(monkeypatch):
@@ -101,9 +129,8 @@ def test_golden_fixture_with_the_cull(monkeypatch, colored):
 
 def test_resident_frames_path_with_the_cull(monkeypatch):
     # frames already in HBM (the fused kernel, SELECT = false): amb_ortho_process_device
-    if os.environ.get("AMB_TEST_EMU", "0") not in ("", "0"):
-        pytest.skip("needs real device pointers (torch.cuda); tests/test_emulated_kernels.py covers the fused kernel")
-    torch = pytest.importorskip("torch")
+    emulated = os.environ.get("AMB_TEST_EMU", "0") not in ("", "0")   # tests/emu: host memory IS device memory
+    torch = None if emulated else pytest.importorskip("torch")
     rows, cols, res = 256, 192, 0.5
     camd, poses, imgs = make_inputs(rows, cols, res, 3, 5, 60.0, 0.1, False)
     elev = synth.analytic_elevation(rows, cols, res)
@@ -113,9 +140,9 @@ def test_resident_frames_path_with_the_cull(monkeypatch):
         gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
         gm["elevation"] = elev
         gm.to_device(0)
-        d_imgs = [torch.from_numpy(im).cuda() for im in imgs]
+        d_imgs = imgs if emulated else [torch.from_numpy(im).cuda() for im in imgs]
         o = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), gm)
-        o.process_device(poses, [t.data_ptr() for t in d_imgs], camd["width"], gm)
+        o.process_device(poses, [im.ctypes.data if emulated else im.data_ptr() for im in d_imgs], camd["width"], gm)
         gm.download()
         outs.append(gm)
     for k in ("ortho", "elevation_angle", "observation_index"):
