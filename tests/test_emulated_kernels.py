@@ -36,6 +36,14 @@ def test_validated_gpu_tests_pass_on_the_emulated_kernels_too():
     assert " passed" in tail and "failed" not in tail
 
 
+@pytest.mark.parametrize("tool,seed,cases", [("emu_fuzz_dsm.py", 11, 6), ("emu_fuzz_ortho.py", 12, 8)])
+def test_random_cases_on_the_emulated_kernels(tool, seed, cases):
+    # tools/emu_fuzz_*.py: random geometry / density / cameras (from 1x1 maps up) against the oracle
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), str(seed), str(cases)], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "fails 0" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
 def test_the_product_never_reaches_for_the_emulated_library():
     pkg = os.path.join(ROOT, "aerial_mapper_b200")
     for dirpath, _, files in os.walk(pkg):
