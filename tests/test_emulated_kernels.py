@@ -44,6 +44,37 @@ def test_random_cases_on_the_emulated_kernels(tool, seed, cases):
     assert r.returncode == 0 and "fails 0" in r.stdout, (r.stdout + r.stderr)[-2000:]
 
 
+@pytest.mark.parametrize("colored", [False, True])
+def test_cpp_shim_on_the_emulated_kernels_equals_the_reference_build_of_the_same_source(tmp_path, colored):
+    # tests/cpp/shim_demo.cc built against the DROP-IN headers + the emulated kernels vs built against the reference's own
+    # headers and sources (oracle/_ref): the C++ marshalling of the shim is exercised end to end without a GPU
+    import numpy as np
+    import test_shim as ts
+    from common import ulp_diff
+    from oracle import pyoracle as po
+    if not po.have_reference_demo():
+        pytest.skip("oracle/_ref/libamb_reference_demo.so not built (needs /root/reference)")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    libdir = os.path.dirname(build_emu.build())
+    exe = str(tmp_path / "shim_demo_emu")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-DAMB_SHIM_MINI", "-I" + os.path.join(ROOT, "aerial_mapper_b200", "shim"),
+                           os.path.join(ROOT, "tests", "cpp", "shim_demo.cc"), "-o", exe, "-L" + libdir, "-lamb_emu",
+                           "-Wl,-rpath," + libdir])
+    scen, (rows, cols, res, xyz, camd, poses, imgs) = ts.make_scenario(tmp_path, colored)
+    out = tmp_path / "layers.bin"
+    r = subprocess.run([exe, str(scen), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    emu = ts.read_layers(out, rows, cols)
+    ref = ts.run_reference_demo(tmp_path, scen, rows, cols)
+    assert np.array_equal(np.isnan(emu[0]), np.isnan(ref[0])) and ulp_diff(emu[0], ref[0]).max() <= 1
+    same = (emu[2] == ref[2]) | (np.isnan(emu[2]) & np.isnan(ref[2]))
+    assert (~same).sum() <= 2
+    for k in (3, 4):
+        assert (emu[k].view(np.uint32) != ref[k].view(np.uint32))[same].sum() == 0
+    assert ulp_diff(emu[1][same], ref[1][same]).max() <= 1
+
+
 def test_the_product_never_reaches_for_the_emulated_library():
     pkg = os.path.join(ROOT, "aerial_mapper_b200")
     for dirpath, _, files in os.walk(pkg):
