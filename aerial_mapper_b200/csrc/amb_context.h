@@ -13,7 +13,11 @@
 
 namespace amb {
 
+#ifdef AMB_CUDA_EMU  // tests/emu (CPU emulation of the kernel source): grid-stride launches need no more blocks than this
+constexpr int kNumSMsB200 = 2;
+#else
 constexpr int kNumSMsB200 = 148;
+#endif
 
 // A grow-only device buffer: process() is called repeatedly on the same context (incremental mapping,
 // main-ortho-backward-grid-incremental.cc:143-163), so scratch is allocated once and kept.

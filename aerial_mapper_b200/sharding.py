@@ -115,7 +115,7 @@ class HaloExchange(object):
         with self._on_stream():
             self.send.fill_(float("nan"))
         if not shared:
-            self.torch.cuda.current_stream().synchronize()
+            self._host_sync()
         base = self.send.data_ptr()
         check(lib().amb_dsm_extract_halo(ctx, C.c_void_p(self.local_xyz.data_ptr()),
                                          C.c_void_p(self.local_ids.data_ptr()), self.n_local, float(y_lo),
@@ -136,6 +136,11 @@ class HaloExchange(object):
             self.big_ids[:w * cap] = self.gathered[:, 3 * cap:4 * cap].reshape(-1).view(self.torch.int64)
             self.big_xyz[self.rank * cap:(self.rank + 1) * cap] = float("nan")  # own halo: already local
         if getattr(self, "stream", None) is None:
+            self._host_sync()
+
+    def _host_sync(self):
+        """Wait for the torch-side work on the current stream (nothing to wait for with host tensors)."""
+        if self.send.is_cuda:
             self.torch.cuda.current_stream().synchronize()
 
     def counts(self):

@@ -1,7 +1,7 @@
 // emu_runtime.cc — the fiber scheduler behind tests/emu/include/cuda_runtime.h (TEST INFRASTRUCTURE ONLY).
+// Fibers switch with a dozen instructions of x86-64 assembly (callee-saved registers + stack pointer); ucontext's
+// swapcontext costs a signal-mask system call per switch, and a warp-per-cell kernel switches ~10^7 times.
 #include <cuda_runtime.h>
-
-#include <ucontext.h>
 
 #include <chrono>
 #include <map>
@@ -29,7 +29,7 @@ struct Warp {
   bool pred[32];
 };
 struct Fiber {
-  ucontext_t ctx;
+  void* sp = nullptr;  // saved stack pointer while the fiber is not running
   char* stack = nullptr;
   bool done = false;
 };
@@ -39,14 +39,38 @@ int g_n = 0;
 std::vector<Warp> g_warps;
 Barrier g_block;
 int g_block_count_acc = 0, g_block_count_result = 0;
-ucontext_t g_scheduler;
+void* g_scheduler_sp = nullptr;
 int g_current = -1;
 unsigned long long g_progress = 0;  // bumped whenever a barrier releases or a fiber finishes
 const std::function<void()>* g_body = nullptr;
 std::vector<unsigned char> g_dyn_smem;
 unsigned char* g_dyn_ptr = nullptr;
 
-void yield() { swapcontext(&g_fibers[g_current].ctx, &g_scheduler); }
+extern "C" void amb_emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl amb_emu_switch
+.type amb_emu_switch,@function
+amb_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size amb_emu_switch,.-amb_emu_switch
+)");
+
+void yield() { amb_emu_switch(&g_fibers[g_current].sp, g_scheduler_sp); }
 
 void arrive_and_wait(Barrier& b) {
   const unsigned long long gen = b.generation;
@@ -75,7 +99,17 @@ void fiber_main() {
   ++g_progress;
   leave(g_block);
   leave(g_warps[g_current >> 5].bar);
-  swapcontext(&f.ctx, &g_scheduler);  // never resumed
+  amb_emu_switch(&f.sp, g_scheduler_sp);  // never resumed
+  std::abort();
+}
+
+void prepare(Fiber& f) {  // a fresh stack whose first switch-in "returns" into fiber_main
+  uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + kStackBytes) & ~uintptr_t(15);
+  void** sp = reinterpret_cast<void**>(top - 64);
+  for (int k = 0; k < 6; ++k) sp[k] = nullptr;           // r15 r14 r13 r12 rbx rbp
+  sp[6] = reinterpret_cast<void*>(&fiber_main);          // return address of the first switch
+  sp[7] = nullptr;                                       // fiber_main's own (never used) return address
+  f.sp = sp;
 }
 
 }  // namespace
@@ -161,11 +195,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     for (int t = 0; t < n; ++t) {
       Fiber& f = g_fibers[t];
       f.done = false;
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack;
-      f.ctx.uc_stack.ss_size = kStackBytes;
-      f.ctx.uc_link = nullptr;
-      makecontext(&f.ctx, fiber_main, 0);
+      prepare(f);
       ++g_warps[t >> 5].bar.alive;
     }
     int remaining = n;
@@ -178,7 +208,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         threadIdx = uint3{static_cast<unsigned int>(t) % block.x, (static_cast<unsigned int>(t) / block.x) % block.y,
                           static_cast<unsigned int>(t) / (block.x * block.y)};
         blockIdx = uint3{b, 0, 0};
-        swapcontext(&g_scheduler, &g_fibers[t].ctx);
+        amb_emu_switch(&g_scheduler_sp, g_fibers[t].sp);
         if (!g_fibers[t].done) ++remaining;
       }
       if (remaining > 0 && g_progress == before) {

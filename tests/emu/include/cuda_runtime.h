@@ -4,7 +4,7 @@
 // The product package never loads that library and the bench never does; a test has to swap it in explicitly.
 //
 // Execution model: one OS thread; a launch runs its blocks one after the other; the threads of a block are fibers
-// (ucontext) scheduled round-robin, each running until it reaches a block barrier or a warp collective.
+// (a minimal x86-64 context switch) scheduled round-robin, each running until it reaches a block barrier or a warp collective.
 //   __syncthreads / __syncthreads_count     all live threads of the block
 //   __shfl*_sync, __ballot_sync, __any_sync, __syncwarp   all live lanes of the warp (masks are assumed full)
 // Threads that have returned no longer count.  A round in which no fiber makes progress is reported as a deadlock.

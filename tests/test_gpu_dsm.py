@@ -241,11 +241,16 @@ def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map(o
     amb_dsm_extract_halo and exchanged (here: three ranks simulated one after the other on one GPU)."""
     import torch
     from aerial_mapper_b200 import sharding
+    # tests/emu (AMB_TEST_EMU=1, the kernel source on a CPU): host memory is "device" memory there, so CPU tensors do
+    emulated = os.environ.get("AMB_TEST_EMU", "0") not in ("", "0")
+    if emulated and on_library_stream:
+        pytest.skip("torch.cuda.ExternalStream needs a real device")
     rows, cols, res, world = 150, 200, 0.5, 3
     xyz_np = synth.point_cloud(120000, rows * res / 2 + 3.0, cols * res / 2 + 3.0, seed=71, holes=5,
                                hole_sides=(3.0, 12.0))
     full, _ = gpu_dsm(rows, cols, res, xyz_np)
-    dev = torch.device("cuda:0")
+    dev = torch.device("cpu" if emulated else "cuda:0")
+    device_sync = (lambda: None) if emulated else torch.cuda.synchronize
     xyz = torch.from_numpy(xyz_np).to(dev)
     ids = torch.arange(xyz.shape[0], dtype=torch.int64, device=dev)
     gms, exch = [], []
@@ -264,14 +269,14 @@ def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map(o
         gms.append((gm, c0, c1))
         exch.append(hx)
     assert sum(h.n_local for h in exch) == xyz.shape[0]          # the stripes partition the cloud
-    torch.cuda.synchronize()
+    device_sync()
     for gm, _, _ in gms:
         gm.sync()
     gathered = torch.stack([h.send for h in exch])               # what the all-gather would deliver
-    torch.cuda.synchronize()
+    device_sync()
     for r, (hx, (gm, c0, c1)) in enumerate(zip(exch, gms)):
         hx.gathered.copy_(gathered)
-        torch.cuda.synchronize()
+        device_sync()
         assert (hx.counts() <= hx.cap).all() and (hx.counts() > 0).all()
         hx.assemble()
         d = amb.Dsm(amb.DsmSettings(), gm)
