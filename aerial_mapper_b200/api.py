@@ -247,6 +247,9 @@ class Dsm(object):
         self.settings_ = settings
         self.debug = False
         self.last_debug = None
+        # opt-in load-balanced gather (amb_dsm_set_balanced_gather); AMB_DSM_BALANCED_GATHER=1 turns it on for every
+        # instance (how the pending GPU tests and the bench exercise it before it may become the default)
+        self.balanced_gather = os.environ.get("AMB_DSM_BALANCED_GATHER", "0") not in ("", "0")
 
     def process(self, point_cloud, map):
         """point_cloud: float64 [n, 3] (the AoS layout of std::vector<Eigen::Vector3d>).  Mutates map['elevation']."""
@@ -262,6 +265,7 @@ class Dsm(object):
         if not map.is_resident():
             map.upload(("elevation",))
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
+        check(lib().amb_dsm_set_balanced_gather(ctx, 1 if self.balanced_gather else 0), ctx)
         check(lib().amb_dsm_process(ctx, pc.ctypes.data_as(C.c_void_p), n, int(s.interpolation_radius),
                                     float(s.center_easting), float(s.center_northing)), ctx)
         self._fetch_debug(map)
@@ -277,6 +281,7 @@ class Dsm(object):
         ctx = map.context()
         s = self.settings_
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
+        check(lib().amb_dsm_set_balanced_gather(ctx, 1 if self.balanced_gather else 0), ctx)
         if d_ids is None:
             check(lib().amb_dsm_process_device(ctx, C.c_void_p(int(d_xyz)), int(n), int(s.interpolation_radius),
                                                float(s.center_easting), float(s.center_northing)), ctx)

@@ -351,6 +351,12 @@ int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* i
   return AMB_OK;
 }
 
+int amb_dsm_set_balanced_gather(amb_ctx* ctx, int enable) {
+  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->dsm_gather_balanced = enable != 0;
+  return AMB_OK;
+}
+
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell) {
   if (!ctx || !(points_per_cell >= 0.0)) return AMB_ERR_INVALID_ARGUMENT;
   ctx->dsm_density_hint = points_per_cell;

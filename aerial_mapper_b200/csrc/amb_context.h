@@ -125,6 +125,7 @@ struct amb_ctx {
   amb::DeviceBuffer dbg_level;    // int8 per slab cell
   double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
+  bool dsm_gather_balanced = false;  // opt-in: dsm_gather_kernel_bal (strips handed to threads by candidate count)
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;
   std::vector<unsigned char> last_dsm_plan;  // the DsmPlan of the last dsm_run (read by the adaptive OrthoFromPcl pass)

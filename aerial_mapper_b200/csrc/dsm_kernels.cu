@@ -326,295 +326,28 @@ struct GatherArgs {
   int tiles_i;
 };
 
-// Per-thread work of the gather kernel.  A thread owns kStrip cells with the same i and adjacent j; their windows
-// overlap in all but one bin row, so every staged point is loaded once, (qx - px)^2 is computed once, and only
-// the (qy - py)^2 + compare + accumulate part is per cell.  The thread walks the kStrip + 2W bin rows of its
-// strip as ONE flattened loop (lanes stay busy until their own candidates run out); `srow[r]` is the half-width
-// of the widest window among the strip's cells on row r.
-// Accumulation order per cell: bin rows ascending, points ascending inside a row == canonical order.
-// Shared memory is addressed by byte offset (plain LDS, no generic pointers):
-//   off_A    uint32 A[NJw*NIw + 2]: A[lin] = start of bin lin, A[lin + 1] = its end (bins are i-fastest)
-template <bool DEBUG>
-__device__ __forceinline__ void gather_strip(const DsmPlan& plan, const GatherArgs& args, int off_A, int off_srow,
-                                             int off_sxy, int off_spz, int i0, int jl0_tile) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int W = plan.W;
-  const int NIw = TI + 2 * W;
-  const int ti = threadIdx.x & 31;
-  const int tq = threadIdx.x >> 5;  // warp index == strip index along j (warp-uniform)
-  const int i = i0 + ti;
-  const int jl0 = jl0_tile + kStrip * tq;  // slab-local column of the strip's first cell (< 0 left of the stripe)
-  const double qx = cell_x(plan, i);
-  const double thr0 = plan.thr0;
-  double qy[kStrip], num[kStrip], den[kStrip];
-  int cnt[kStrip];
-  unsigned int cellmask = 0;
-#pragma unroll
-  for (int m = 0; m < kStrip; ++m) {
-    qy[m] = cell_y(plan, plan.col_begin + jl0 + m);
-    num[m] = 0.0;
-    den[m] = 0.0;
-    cnt[m] = 0;
-    if (i < plan.rows && jl0 + m >= 0 && jl0 + m < plan.cols_slab) cellmask |= 1u << m;
-  }
-  const int n_rows = kStrip + 2 * W;
-  int r = -1;                                                      // row of the strip's window
-  int lin_addr = off_A + ((kStrip * tq - 1) * NIw + ti + W) * 4;   // byte offset of A[lin], lin = bin (i, row r)
-  unsigned int k = 0, e = 0;
-  if (cellmask) {
-    for (;;) {
-      if (k >= e) {
-        bool found = false;
-        while (r + 1 < n_rows) {
-          ++r;
-          lin_addr += NIw * 4;
-          const int h = *reinterpret_cast<const int*>(smem_raw + off_srow + 4 * r);
-          if (h < 0) continue;
-          // bins [i - h, i + h] of this row: points [A[lin - h], A[lin + h + 1])
-          k = *reinterpret_cast<const unsigned int*>(smem_raw + lin_addr - 4 * h);
-          e = *reinterpret_cast<const unsigned int*>(smem_raw + lin_addr + 4 * h + 4);
-          if (k < e) {
-            found = true;
-            break;
-          }
-        }
-        if (!found) break;
-      }
-      const double2 p = *reinterpret_cast<const double2*>(smem_raw + off_sxy + 16 * k);
-      const double pz = *reinterpret_cast<const double*>(smem_raw + off_spz + 8 * k);
-      const double dx = qx - p.x;
-      const double dx2 = __dmul_rn(dx, dx);
-      // Branch-free: every cell of the strip tests every staged point of the strip's rows.  A bin row that is out
-      // of a cell's reach (|dj| > W) holds only points with |dy| > sqrt(threshold), so it can never hit; a miss
-      // adds exactly 0 (w = 0: fma(z, 0, num) == num, den + 0 == den), so the sums are bit-identical to
-      // visiting only the reachable rows.
-#pragma unroll
-      for (int m = 0; m < kStrip; ++m) {
-        const double dy = qy[m] - p.y;
-        const double d2 = __dadd_rn(dx2, __dmul_rn(dy, dy));  // L2_Adaptor (nanoflann.hpp:325-328), un-contracted
-        const bool hit = d2 < thr0;                           // RadiusResultSet::addPoint (:156-158)
-        const double w = hit ? fast_rcp(d2) : 0.0;            // 1.0 / distances[i]         (dsm.cc:167)
-        num[m] = fma(pz, w, num[m]);                          // heights[i] / distances[i]  (dsm.cc:166), z * (1/d2)
-        den[m] += w;
-        if (DEBUG) cnt[m] += hit ? 1 : 0;
-      }
-      ++k;
-    }
-  }
-  bool coincident = false;
-#pragma unroll
-  for (int m = 0; m < kStrip; ++m) {
-    const bool valid = (cellmask >> m) & 1u;
-    const size_t cell = static_cast<size_t>(jl0 + m) * plan.rows + i;
-    const bool has = den[m] > 0.0 || den[m] != den[m];  // any hit adds a positive weight (NaN: coincident point)
-    // d2 == 0 (a point exactly on the cell centre) is the only way a weight becomes inf/NaN: any d2 > 0 is
-    // >= 1e-26 for metre-scale coordinates.  Dsm: reference CHECK(distances[i] > 0.0) aborts (dsm.cc:165).
-    // OrthoFromPcl: "perfect match" (ortho-from-pcl.cc:90-96) — resolved by the warp-per-cell kernel.
-    const bool zero_dist = has && !(den[m] < DBL_MAX);
-    const bool to_cell_kernel = valid && (plan.mode == 0 ? !has : zero_dist);
-    if (valid) {
-      if (zero_dist && plan.mode == 0) coincident = true;
-      if (has && !(zero_dist && plan.mode == 1))
-        args.elevation[cell] = __double2float_rn(__ddiv_rn(num[m], den[m]));  // dsm.cc:171-172
-      if (DEBUG) {
-        args.dbg_count[cell] = cnt[m];
-        args.dbg_level[cell] = has ? 0 : -1;
-      }
-    }
-    // cells for the warp-per-cell pass (Dsm: empty primary ball -> retry thresholds): one atomic per warp
-    const unsigned int mask = __ballot_sync(0xffffffffu, to_cell_kernel);
-    if (mask) {
-      const int leader = __ffs(mask) - 1;
-      unsigned int base = 0;
-      if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (to_cell_kernel)
-        args.cell_list[base + __popc(mask & ((1u << ti) - 1u))] = static_cast<unsigned int>(cell);
-    }
-  }
-  if (coincident) atomicExch(&args.counters[1], 1u);
-}
-
-__global__ void __launch_bounds__(kGatherThreads)
-    dsm_gather_kernel(const __grid_constant__ DsmPlan plan, const GatherArgs args) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned int s_total;
-  __shared__ unsigned int s_runs;
-  __shared__ unsigned int s_scan_total;
-  const int W = plan.W;
-  const int NIw = TI + 2 * W, NJw = TJ + 2 * W;  // window of the tile in fine bins
-  const int N = NIw * NJw;
-  const int n_strip_rows = kStrip + 2 * W;
-  // carve: A[N + 2] | srow[kStrip + 2W] | run_pre[max_runs + 1] | run_g0[max_runs] | xy | z | idx
-  unsigned int* A = reinterpret_cast<unsigned int*>(smem_raw);
-  int* srow = reinterpret_cast<int*>(A + N + 2);
-  const int max_runs = (NJw + plan.B - 1) / plan.B + 1;  // bucket rows overlapping the window
-  unsigned int* run_pre = reinterpret_cast<unsigned int*>(srow + n_strip_rows);
-  unsigned int* run_g0 = run_pre + max_runs + 1;
-  size_t off_bytes = (static_cast<size_t>(N) + 2 + n_strip_rows + 2 * max_runs + 1) * 4;
-  off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
-  const int off_sxy = static_cast<int>(off_bytes);
-  const int off_spz = off_sxy + 16 * args.capacity;
-  const int off_sidx = off_spz + 8 * args.capacity;
-  double2* sxy = reinterpret_cast<double2*>(smem_raw + off_sxy);
-  double* spz = reinterpret_cast<double*>(smem_raw + off_spz);
-  unsigned int* sidx = reinterpret_cast<unsigned int*>(smem_raw + off_sidx);
-
-  const int tile_i = blockIdx.x % args.tiles_i;
-  const int tile_j = blockIdx.x / args.tiles_i;
-  const int i0 = tile_i * TI;
-  const int gj_tile = (plan.tile_j0 + tile_j) * TJ;  // global column of the tile's first cell
-  const int jl0_tile = gj_tile - plan.col_begin;      // slab-local (negative if the tile starts left of the stripe)
-  const int wi0 = i0 + plan.Pa - W;                   // window origin in fine bins (>= 0: Pa >= W)
-  const int wj0 = gj_tile - plan.gj0 - W;
-
-  // 0. tables: strip rows, zeroed cell counters, bucket runs (one contiguous record range per bucket row)
-  for (int r = threadIdx.x; r < n_strip_rows; r += kGatherThreads) {
-    // strip row r is bin row (first cell's j) - W + r; cell m of the strip sees it at dj = r - W - m
-    int hmax = -1;
-    for (int m = 0; m < kStrip; ++m) {
-      const int dj = r - W - m;
-      const int ad = dj < 0 ? -dj : dj;
-      const int h = ad <= W ? plan.hw[ad] : -1;
-      hmax = max(hmax, h);
-    }
-    srow[r] = hmax;
-  }
-  for (int e = threadIdx.x; e < N + 2; e += kGatherThreads) A[e] = 0;
-  const int kbi0 = wi0 >> plan.Bshift;
-  const int kbi1 = min(wi0 + NIw - 1, plan.BR - 1) >> plan.Bshift;
-  const int kbj0 = wj0 >> plan.Bshift;
-  const int kbj1 = min(wj0 + NJw - 1, plan.BC - 1) >> plan.Bshift;
-  const int n_runs = kbj1 - kbj0 + 1;
-  if (threadIdx.x == 0) {
-    unsigned int acc = 0;
-    for (int q = 0; q < n_runs; ++q) {
-      const size_t row = static_cast<size_t>(kbj0 + q) * plan.KR;
-      const unsigned int g0 = args.G[row + kbi0];
-      const unsigned int g1 = args.G[row + kbi1 + 1];
-      run_pre[q] = acc;
-      run_g0[q] = g0;
-      acc += g1 - g0;
-    }
-    run_pre[n_runs] = acc;
-    s_runs = acc;
-    s_total = 0;
-  }
-  __syncthreads();
-  const unsigned int n_in = s_runs;  // points of the buckets overlapping the window
-
-  // 1. count the window's points per cell (shared-memory atomics): bin lin is counted in A[2 + lin], so that the
-  //    inclusive scan below leaves A[1 + lin] = start(lin).
-  bool dense = n_in > 4u * static_cast<unsigned int>(args.capacity);  // cannot fit whatever the window keeps
-  if (!dense) {
-    unsigned int kept = 0;
-    for (unsigned int q = threadIdx.x; q < n_in; q += kGatherThreads) {
-      int run = 0;
-      while (q >= run_pre[run + 1]) ++run;
-      const PointRec* pr = args.rec + run_g0[run] + (q - run_pre[run]);
-      const double2 xy = __ldg(reinterpret_cast<const double2*>(pr));
-      int bi, bj;
-      if (fine_bin(plan, xy.x, xy.y, &bi, &bj)) {
-        const int ii = bi - wi0, jj = bj - wj0;
-        if (ii >= 0 && ii < NIw && jj >= 0 && jj < NJw) {
-          atomicAdd(&A[2 + jj * NIw + ii], 1u);
-          ++kept;
-        }
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xffffffffu, kept, o);
-    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&s_total, kept);
-  }
-  __syncthreads();
-  dense = dense || s_total > static_cast<unsigned int>(args.capacity);
-  if (dense) {
-    // Too many points for the stage (density far above the average it was sized for): every cell of the tile is
-    // evaluated by the warp-per-cell kernel instead.  The decision depends only on the tile's points, and tiles
-    // are aligned to global columns, so it is the same for every striping of the map.
-    if (threadIdx.x == 0) atomicAdd(&args.counters[3], 1u);
-    const int ti = threadIdx.x & 31, tq = threadIdx.x >> 5;
-    for (int m = 0; m < kStrip; ++m) {
-      const int i = i0 + ti, jl = jl0_tile + kStrip * tq + m;
-      const bool valid = i < plan.rows && jl >= 0 && jl < plan.cols_slab;
-      const unsigned int mask = __ballot_sync(0xffffffffu, valid);
-      if (mask) {
-        const int leader = __ffs(mask) - 1;
-        unsigned int base = 0;
-        if (ti == leader) base = atomicAdd(&args.counters[0], static_cast<unsigned int>(__popc(mask)));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid)
-          args.cell_list[base + __popc(mask & ((1u << ti) - 1u))] =
-              static_cast<unsigned int>(static_cast<size_t>(jl) * plan.rows + i);
-      }
-    }
-    return;
-  }
-
-  // 2. inclusive scan of A[0 .. N + 1] in place: thread t owns a contiguous chunk
-  {
-    const int per = (N + 2 + kGatherThreads - 1) / kGatherThreads;
-    const int lo = min(static_cast<int>(threadIdx.x) * per, N + 2), hi = min(lo + per, N + 2);
-    unsigned int s = 0;
-    for (int e = lo; e < hi; ++e) s += A[e];
-    unsigned int run = block_exclusive_scan(s, &s_scan_total);
-    for (int e = lo; e < hi; ++e) {
-      run += A[e];
-      A[e] = run;
-    }
-  }
-  __syncthreads();
-
-  // 3. scatter the window's points into cell order: A[1 + lin] is the cursor of bin lin; afterwards
-  //    A[1 + lin] = start(lin + 1), i.e. A[lin] = start(lin) (A[0] = 0) — the layout gather_strip reads.
-  for (unsigned int q = threadIdx.x; q < n_in; q += kGatherThreads) {
-    int run = 0;
-    while (q >= run_pre[run + 1]) ++run;
-    const PointRec* pr = args.rec + run_g0[run] + (q - run_pre[run]);
-    double x, y, z, ib;
-    load_rec(pr, &x, &y, &z, &ib);
-    int bi, bj;
-    if (fine_bin(plan, x, y, &bi, &bj)) {
-      const int ii = bi - wi0, jj = bj - wj0;
-      if (ii >= 0 && ii < NIw && jj >= 0 && jj < NJw) {
-        const unsigned int pos = atomicAdd(&A[1 + jj * NIw + ii], 1u);
-        sxy[pos] = make_double2(x, y);
-        spz[pos] = z;
-        sidx[pos] = static_cast<unsigned int>(__double_as_longlong(ib));
-      }
-    }
-  }
-  __syncthreads();
-
-  // 4. canonical order inside every cell: ascending original index
-  for (int lin = threadIdx.x; lin < N; lin += kGatherThreads) {
-    const unsigned int s = A[lin], e = A[lin + 1];
-    for (unsigned int a = s + 1; a < e; ++a) {
-      const unsigned int key = sidx[a];
-      if (sidx[a - 1] <= key) continue;
-      const double2 kxy = sxy[a];
-      const double kz = spz[a];
-      unsigned int q = a;
-      while (q > s && sidx[q - 1] > key) {
-        sidx[q] = sidx[q - 1];
-        sxy[q] = sxy[q - 1];
-        spz[q] = spz[q - 1];
-        --q;
-      }
-      sidx[q] = key;
-      sxy[q] = kxy;
-      spz[q] = kz;
-    }
-  }
-  __syncthreads();
-
-  // 5. per-cell gather: every thread owns a 1 x kStrip strip of cells (same i, adjacent j)
-  const int off_srow = static_cast<int>(reinterpret_cast<unsigned char*>(srow) - smem_raw);
-  if (args.dbg_count) {  // tests: also record result_set.size() per cell
-    gather_strip<true>(plan, args, 0, off_srow, off_sxy, off_spz, i0, jl0_tile);
-  } else {
-    gather_strip<false>(plan, args, 0, off_srow, off_sxy, off_spz, i0, jl0_tile);
-  }
-}
+#define AMB_GATHER_BALANCED 0
+#define AMB_GATHER_STRIP gather_strip
+#define AMB_GATHER_KERNEL dsm_gather_kernel
+#define AMB_GATHER_STRIP_ID_PARAM
+#define AMB_GATHER_LANE ti
+#include "dsm_gather_body.inc"
+#undef AMB_GATHER_BALANCED
+#undef AMB_GATHER_STRIP
+#undef AMB_GATHER_KERNEL
+#undef AMB_GATHER_STRIP_ID_PARAM
+#undef AMB_GATHER_LANE
+#define AMB_GATHER_BALANCED 1
+#define AMB_GATHER_STRIP gather_strip_bal
+#define AMB_GATHER_KERNEL dsm_gather_kernel_bal
+#define AMB_GATHER_STRIP_ID_PARAM , int strip_id
+#define AMB_GATHER_LANE lane
+#include "dsm_gather_body.inc"
+#undef AMB_GATHER_BALANCED
+#undef AMB_GATHER_STRIP
+#undef AMB_GATHER_KERNEL
+#undef AMB_GATHER_STRIP_ID_PARAM
+#undef AMB_GATHER_LANE
 
 // ---------------------------------------------------------------------------------------------------------------
 // K5: one warp per listed cell.  Evaluates the reference's complete per-cell sequence (primary query, then the
@@ -950,9 +683,15 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   ga.capacity = capacity;
   ga.tiles_i = (plan.rows + TI - 1) / TI;
   const int tiles_j = tile_j1 - plan.tile_j0 + 1;
-  AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-  dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+  if (ctx->dsm_gather_balanced) {  // opt-in (amb_dsm_set_balanced_gather): strips handed out by candidate count
+    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    dsm_gather_kernel_bal<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+  } else {
+    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+  }
   ctx->dsm_launches += 1;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));
 

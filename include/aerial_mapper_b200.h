@@ -175,6 +175,10 @@ int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t
  * rank passes the same global figure to keep all summation orders — every output bit — independent of the
  * sharding.  0 (default): derive it from the points passed to each call. */
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell);
+/* Opt-in (default 0): the gather kernel hands its 1x4-cell strips to threads in order of their number of staged
+ * candidates, so that the lanes of a warp finish together (a warp otherwise waits for the slowest of 32 Poisson-distributed
+ * strips).  Same output bits: every cell is still summed by one thread in canonical order. */
+int amb_dsm_set_balanced_gather(amb_ctx* ctx, int enable);
 /* The y-interval (y_lo, y_hi] covered by the cells of columns [col_begin, col_end) (points are assigned to the
  * rank whose interval holds y - center_easting), and how far a point can act across a stripe border. */
 int amb_stripe_y_interval(const amb_geometry* geom, int32_t col_begin, int32_t col_end, double* y_lo, double* y_hi);

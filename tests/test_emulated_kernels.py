@@ -3,7 +3,7 @@ CUDA runtime (tests/emu/README.md — test infrastructure only, never a fallback
 normal Python mirror + C ABI by the GPU tests themselves, in a child pytest process with AMB_TEST_EMU=1.
 
   * every `gpu_pending` test (kernels written after the round's GPU budget was spent: the orthomosaic's dominance cull,
-    OrthoFromPcl's adaptive interpolation, the stereo rectification maps), and
+    the DSM's load-balanced gather, OrthoFromPcl's adaptive interpolation, the stereo rectification maps), and
   * the already validated `gpu` tests (all but the few that create inputs with torch.cuda): the emulation reproduces
     what the B200 produced — and re-checks, on every CPU run, the CURRENT sources' kernel and host logic.
 This does not replace a GPU run (fibers run one after the other: no races, no memory model, no performance)."""
@@ -28,7 +28,8 @@ def run_child(marker, files, extra=()):
 
 
 def test_pending_gpu_tests_pass_on_the_emulated_kernels():
-    tail = run_child("gpu_pending", ["test_gpu_ortho_dominance.py", "test_ortho_from_pcl.py", "test_stereo_rectify.py"])
+    tail = run_child("gpu_pending", ["test_gpu_ortho_dominance.py", "test_gpu_dsm_balanced.py", "test_ortho_from_pcl.py",
+                                     "test_stereo_rectify.py"])
     assert " passed" in tail and "failed" not in tail
 
 
