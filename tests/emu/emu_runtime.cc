@@ -3,6 +3,7 @@
 // swapcontext costs a signal-mask system call per switch, and a warp-per-cell kernel switches ~10^7 times.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <string>
@@ -36,6 +37,8 @@ struct Fiber {
 
 std::vector<Fiber> g_fibers;  // pool; the first g_n belong to the running block
 int g_n = 0;
+int g_sched_mode = -1;  // 0 ascending, 1 reverse, 2 pseudo-random permutation (changes every round)
+unsigned long long g_sched_stride = 1, g_sched_offset = 0, g_sched_state = 0x9e3779b97f4a7c15ull;
 std::vector<Warp> g_warps;
 Barrier g_block;
 int g_block_count_acc = 0, g_block_count_result = 0;
@@ -175,6 +178,11 @@ unsigned int warp_ballot(bool pred) {
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   const int n = static_cast<int>(block.x * block.y * block.z);
   if (n <= 0 || grid.x == 0) return;
+  if (g_sched_mode < 0) {
+    const char* m = std::getenv("AMB_EMU_SCHED");
+    g_sched_mode = (m && std::string(m) == "reverse") ? 1 : (m && std::string(m).rfind("random", 0) == 0) ? 2 : 0;
+    if (g_sched_mode == 2 && std::strlen(m) > 7) g_sched_state ^= std::strtoull(m + 7, nullptr, 10) * 0x2545f4914f6cdd1dull;
+  }
   if (static_cast<int>(g_fibers.size()) < n) {
     const size_t old = g_fibers.size();
     g_fibers.resize(n);
@@ -202,7 +210,22 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     while (remaining > 0) {
       const unsigned long long before = g_progress;
       remaining = 0;
-      for (int t = 0; t < n; ++t) {
+      if (g_sched_mode == 2) {  // t = (slot * stride + offset) mod n with an odd stride coprime to n: a permutation
+        g_sched_state = g_sched_state * 6364136223846793005ull + 1442695040888963407ull;
+        g_sched_stride = ((g_sched_state >> 33) % static_cast<unsigned long long>(n)) | 1ull;
+        while (std::__gcd(g_sched_stride, static_cast<unsigned long long>(n)) != 1ull) g_sched_stride += 2;
+        g_sched_offset = (g_sched_state >> 13) % static_cast<unsigned long long>(n);
+      }
+      for (int slot = 0; slot < n; ++slot) {
+        // AMB_EMU_SCHED: the order in which the threads of a block get their turn (default ascending).  A kernel must not
+        // care; a missing barrier between a write and another thread's read shows up as a changed result under
+        // `reverse` or `random` (tests/test_emulated_kernels.py runs the pending kernels under all three).
+        int t = slot;
+        if (g_sched_mode == 1) {
+          t = n - 1 - slot;
+        } else if (g_sched_mode == 2) {
+          t = static_cast<int>((static_cast<unsigned long long>(slot) * g_sched_stride + g_sched_offset) % n);
+        }
         if (g_fibers[t].done) continue;
         g_current = t;
         threadIdx = uint3{static_cast<unsigned int>(t) % block.x, (static_cast<unsigned int>(t) / block.x) % block.y,

@@ -16,9 +16,13 @@ import pytest
 from common import ROOT
 
 
-def run_child(marker, files, extra=()):
+def run_child(marker, files, extra=(), sched=None):
     env = dict(os.environ, AMB_TEST_EMU="1")
     env.pop("AMB_ORTHO_DOMINANCE", None)
+    env.pop("AMB_DSM_BALANCED_GATHER", None)
+    env.pop("AMB_EMU_SCHED", None)
+    if sched:
+        env["AMB_EMU_SCHED"] = sched   # order in which the threads of a block take their turns (tests/emu/emu_runtime.cc)
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", marker, "-p", "no:cacheprovider"] + list(extra) + \
           [os.path.join(ROOT, "tests", f) for f in files]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True)
@@ -27,9 +31,12 @@ def run_child(marker, files, extra=()):
     return tail
 
 
-def test_pending_gpu_tests_pass_on_the_emulated_kernels():
+@pytest.mark.parametrize("sched", [None, "reverse", "random:5"])
+def test_pending_gpu_tests_pass_on_the_emulated_kernels(sched):
+    # also with the block's threads scheduled in reverse and in a fresh pseudo-random order every round: a kernel whose
+    # result depended on who runs first (e.g. a missing barrier between a write and another thread's read) would differ
     tail = run_child("gpu_pending", ["test_gpu_ortho_dominance.py", "test_gpu_dsm_balanced.py", "test_ortho_from_pcl.py",
-                                     "test_stereo_rectify.py"])
+                                     "test_stereo_rectify.py"], sched=sched)
     assert " passed" in tail and "failed" not in tail
 
 
