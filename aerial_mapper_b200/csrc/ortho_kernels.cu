@@ -74,6 +74,7 @@ struct OrthoArgs {
   double ui_lo, ui_hi, vi_lo, vi_hi;
   double nui_lo, nui_hi, nvi_lo, nvi_hi;  // sqrt(1 + bound^2)
   double dom_margin;                      // rad
+  double dom_theta_in;                    // equidistant: every ray with angle-to-axis below this is imaged (else unused)
 };
 
 // Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed + one cubic correction step.
@@ -452,7 +453,31 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   // non-empty INNER rectangle — the raster's normalised extent shrunk by the same distortion bound E the outer
   // rectangle was grown by: a ray with an undistorted keypoint inside it is imaged inside the raster.
   bool dominance = false;
-  if (ctx->ortho_dominance && a.do_cull && a.rect && a.dist_type != AMB_DIST_EQUIDISTANT) {
+  if (ctx->ortho_dominance && a.do_cull && a.cone && !a.rect && a.dist_type == AMB_DIST_EQUIDISTANT) {
+    // Equidistant: the keypoint's distance from the principal point (normalised) is |theta * poly(theta^2)| whatever the
+    // azimuth, so every ray with theta <= theta_in is imaged if that radius stays below the distance to the nearest
+    // raster edge on [0, theta_in].  Scan outwards with a Lipschitz bound on the radius; stop at the first step that
+    // might leave the inscribed circle.
+    const double* k = camera->dist;
+    const double r_in = std::min(std::min(camera->cu, camera->width - camera->cu) / std::fabs(camera->fu),
+                                 std::min(camera->cv, camera->height - camera->cv) / std::fabs(camera->fv)) * (1.0 - 1e-9);
+    const double step = 1e-4;
+    double th = 0.0;
+    while (th < 1.5) {
+      const double b = th + step, b2 = b * b;
+      const double lip = 1.0 + 3.0 * std::fabs(k[0]) * b2 + 5.0 * std::fabs(k[1]) * b2 * b2 +
+                         7.0 * std::fabs(k[2]) * b2 * b2 * b2 + 9.0 * std::fabs(k[3]) * b2 * b2 * b2 * b2;  // >= |d r / d theta|
+      const double t2 = th * th;
+      const double r_th = std::fabs(th * (1.0 + k[0] * t2 + k[1] * t2 * t2 + k[2] * t2 * t2 * t2 + k[3] * t2 * t2 * t2 * t2));
+      if (r_th + lip * step >= r_in) break;
+      th = b;
+    }
+    if (th > 1e-3 && camera->fu > 0.0 && camera->fv > 0.0) {
+      a.dom_theta_in = th;
+      a.dom_margin = 1e-4;
+      dominance = true;
+    }
+  } else if (ctx->ortho_dominance && a.do_cull && a.rect && a.dist_type != AMB_DIST_EQUIDISTANT) {
     const double E_u = a.u_hi - (camera->width - camera->cu) / camera->fu;   // what compute_view_rect added
     const double E_v = a.v_hi - (camera->height - camera->cv) / camera->fv;
     const double E = std::max(E_u, E_v) * (1.0 + 1e-9) + 1e-9;
@@ -485,15 +510,19 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.images = ctx->frame_table.as<const uint8_t*>() + f0;
     a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
     const int grid = tiles_i * tiles_j;
-    if (dominance) {  // pinhole / rad-tan only (see above)
+    if (dominance) {
       if (select_only) {
         if (a.dist_type == AMB_DIST_RADTAN) {
           ortho_kernel_dom<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
+        } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
+          ortho_kernel_dom<AMB_DIST_EQUIDISTANT, true><<<grid, kOrthoThreads, 0, s>>>(a);
         } else {
           ortho_kernel_dom<AMB_DIST_NONE, true><<<grid, kOrthoThreads, 0, s>>>(a);
         }
       } else if (a.dist_type == AMB_DIST_RADTAN) {
         ortho_kernel_dom<AMB_DIST_RADTAN, false><<<grid, kOrthoThreads, 0, s>>>(a);
+      } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
+        ortho_kernel_dom<AMB_DIST_EQUIDISTANT, false><<<grid, kOrthoThreads, 0, s>>>(a);
       } else {
         ortho_kernel_dom<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
       }

@@ -274,7 +274,7 @@ int amb_ortho_process_device(amb_ctx* ctx, const amb_camera* camera, const doubl
 /* 0 = cull frames per tile with the conservative view-cone test (default), 1 = brute force over all frames
  * (the cull's own correctness reference). */
 int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force);
-/* Opt-in (default 0): per-tile DOMINANCE cull of the frame list, pinhole / rad-tan cameras.  A frame whose largest
+/* Opt-in (default 0): per-tile DOMINANCE cull of the frame list.  A frame whose largest
  * possible observation angle over the tile is smaller — by a margin far above float32 rounding — than the smallest
  * possible one of a frame that sees every landmark of the tile can never end up as the winner of the reference's
  * running-maximum recurrence (ortho-backward-grid.cc:173-183) nor change who does, so it is not evaluated: same output

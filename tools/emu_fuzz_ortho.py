@@ -16,6 +16,7 @@ from common import ulp_diff, fresh_layers
 from scipy.spatial.transform import Rotation as R
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 fails = 0
+checked = 0
 t0 = time.time()
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 for it in range(N):
@@ -55,7 +56,9 @@ for it in range(N):
         except amb.AmbError as e:
             print("it", it, "AmbError", e); break
         outs.append(gm)
-    if len(outs) < 2: continue
+    if len(outs) < 2:
+        print('case', it, 'skipped: only', len(outs), 'runs', gm.getSize(), (rows, cols)); continue
+    checked += 1
     L = fresh_layers(rows, cols, elev)
     if prior: L["elevation_angle"][...] = np.float32(1.2)
     st, _ = po.ortho_process(po.make_geometry(rows, cols, res), L, po.make_camera(**camd), poses, imgs, colored=colored, num_threads=-1)
@@ -66,5 +69,5 @@ for it in range(N):
         if not ok:
             fails += 1
             print("MISMATCH", nm, "it", it, (rows, cols, res, dist_type, dist, colored, scale, agl, lines, per, prior), "st", st)
-print("done", N, "cases, fails", fails, "%.0fs" % (time.time() - t0))
-sys.exit(1 if fails else 0)
+print("done", N, "cases,", checked, "checked, fails", fails, "%.0fs" % (time.time() - t0))
+sys.exit(1 if fails or checked < N // 2 else 0)
