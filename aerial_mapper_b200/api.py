@@ -250,6 +250,8 @@ class Dsm(object):
         # opt-in load-balanced gather (amb_dsm_set_balanced_gather); AMB_DSM_BALANCED_GATHER=1 turns it on for every
         # instance (how the pending GPU tests and the bench exercise it before it may become the default)
         self.balanced_gather = os.environ.get("AMB_DSM_BALANCED_GATHER", "0") not in ("", "0")
+        # opt-in chunked evaluation + early mirroring of finished columns (amb_dsm_set_stream_chunks); 1 = off
+        self.stream_chunks = max(1, int(os.environ.get("AMB_DSM_STREAM_CHUNKS", "1") or 1))
 
     def process(self, point_cloud, map):
         """point_cloud: float64 [n, 3] (the AoS layout of std::vector<Eigen::Vector3d>).  Mutates map['elevation']."""
@@ -266,6 +268,7 @@ class Dsm(object):
             map.upload(("elevation",))
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
         check(lib().amb_dsm_set_balanced_gather(ctx, 1 if self.balanced_gather else 0), ctx)
+        check(lib().amb_dsm_set_stream_chunks(ctx, int(self.stream_chunks)), ctx)
         check(lib().amb_dsm_process(ctx, pc.ctypes.data_as(C.c_void_p), n, int(s.interpolation_radius),
                                     float(s.center_easting), float(s.center_northing)), ctx)
         self._fetch_debug(map)
@@ -282,6 +285,7 @@ class Dsm(object):
         s = self.settings_
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
         check(lib().amb_dsm_set_balanced_gather(ctx, 1 if self.balanced_gather else 0), ctx)
+        check(lib().amb_dsm_set_stream_chunks(ctx, int(self.stream_chunks)), ctx)
         if d_ids is None:
             check(lib().amb_dsm_process_device(ctx, C.c_void_p(int(d_xyz)), int(n), int(s.interpolation_radius),
                                                float(s.center_easting), float(s.center_northing)), ctx)

@@ -36,6 +36,24 @@ int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab) {
   return AMB_OK;
 }
 
+// Columns [col0, col1) of the slab (slab-local) to the layer's host mirror: the part of a layer that is already final
+// while the rest is still being computed (chunked DSM, amb_dsm_set_stream_chunks).  Contiguous: layers are column-major.
+int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1) {
+  if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer] || col1 <= col0)
+    return AMB_OK;
+  const size_t off = static_cast<size_t>(ctx->geom.rows) * static_cast<size_t>(col0);
+  const size_t cnt = static_cast<size_t>(ctx->geom.rows) * static_cast<size_t>(col1 - col0);
+  AMB_CUDA(ctx, cudaEventRecord(ctx->copy_done[0], ctx->stream));
+  AMB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[0], 0));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->host_mirror[layer] + off, ctx->layers[layer] + off, cnt * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (!ctx->layer_copy_event[layer])
+    AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->layer_copy_event[layer], cudaEventDisableTiming));
+  AMB_CUDA(ctx, cudaEventRecord(ctx->layer_copy_event[layer], ctx->copy_stream));
+  ctx->layer_copy_pending[layer] = true;
+  return AMB_OK;
+}
+
 int mirror_layer(amb_ctx* ctx, int layer) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer]) return AMB_OK;
   return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
@@ -348,6 +366,12 @@ int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* i
   ctx->dsm_timed = (st == AMB_OK);
   if (st != AMB_OK) return st;
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMB_OK;
+}
+
+int amb_dsm_set_stream_chunks(amb_ctx* ctx, int chunks) {
+  if (!ctx || chunks < 1) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->dsm_stream_chunks = chunks;
   return AMB_OK;
 }
 

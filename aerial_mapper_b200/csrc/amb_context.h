@@ -125,6 +125,7 @@ struct amb_ctx {
   amb::DeviceBuffer dbg_level;    // int8 per slab cell
   double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
+  int dsm_stream_chunks = 1;  // opt-in (> 1): gather + fill in column chunks, each chunk's result mirrored to the host at once
   bool dsm_gather_balanced = false;  // opt-in: dsm_gather_kernel_bal (strips handed to threads by candidate count)
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;
@@ -163,7 +164,8 @@ inline int fail(amb_ctx* ctx, cudaError_t e, const char* what) {
 int ensure_layer(amb_ctx* ctx, int layer);
 int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for its pending asynchronous download
 int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab);  // on the copy stream, after current work
-int mirror_layer(amb_ctx* ctx, int layer);     // enqueue_layer_download to the registered host mirror, if any
+int mirror_layer(amb_ctx* ctx, int layer);
+int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1);  // slab-local column range     // enqueue_layer_download to the registered host mirror, if any
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,

@@ -683,33 +683,80 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   ga.capacity = capacity;
   ga.tiles_i = (plan.rows + TI - 1) / TI;
   const int tiles_j = tile_j1 - plan.tile_j0 + 1;
-  if (ctx->dsm_gather_balanced) {  // opt-in (amb_dsm_set_balanced_gather): strips handed out by candidate count
-    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    dsm_gather_kernel_bal<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+  // Opt-in chunking (amb_dsm_set_stream_chunks, only with a registered host mirror): the tile columns are evaluated in K
+  // groups — gather + warp-per-cell fill per group — and each group's finished columns start travelling to the host
+  // at once, so the download of the layer overlaps the evaluation of the remaining groups.  The launches of a group are
+  // the un-chunked ones restricted to its tile columns (plan.tile_j0 and the grid size), so every result is unchanged.
+  const int chunks = (ctx->dsm_stream_chunks > 1 && ctx->host_mirror[out_layer]) ? std::min(ctx->dsm_stream_chunks, tiles_j) : 1;
+  if (chunks > 1) {
+    if (ctx->dsm_gather_balanced) {
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    } else {
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    }
+    CellArgs ca;
+    ca.G = G;
+    ca.order = ctx->point_order.as<unsigned int>();
+    ca.rec = rec;
+    ca.elevation = ga.elevation;
+    ca.cell_list = ga.cell_list;
+    ca.counters = counters;
+    ca.dbg_count = ga.dbg_count;
+    ca.dbg_level = ga.dbg_level;
+    for (int c = 0; c < chunks; ++c) {
+      const int tj0 = static_cast<int>(static_cast<long long>(tiles_j) * c / chunks);
+      const int tj1 = static_cast<int>(static_cast<long long>(tiles_j) * (c + 1) / chunks);
+      if (tj1 <= tj0) continue;
+      DsmPlan pc = plan;
+      pc.tile_j0 = plan.tile_j0 + tj0;
+      if (c > 0) AMB_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(unsigned int), s));  // the cell list restarts
+      if (ctx->dsm_gather_balanced) {
+        dsm_gather_kernel_bal<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
+      } else {
+        dsm_gather_kernel<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
+      }
+      dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(pc, ca);
+      ctx->dsm_launches += 2;
+      // slab-local columns of this group's tiles (tiles are aligned to GLOBAL columns)
+      const int col0 = std::max((plan.tile_j0 + tj0) * TJ - ctx->col_begin, 0);
+      const int col1 = std::min((plan.tile_j0 + tj1) * TJ - ctx->col_begin, ctx->col_end - ctx->col_begin);
+      st = mirror_layer_columns(ctx, out_layer, col0, col1);
+      if (st != AMB_OK) return st;
+    }
+    AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));  // (stage split not meaningful when chunked)
+    AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
+    AMB_CUDA(ctx, cudaGetLastError());
   } else {
-    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
-  }
-  ctx->dsm_launches += 1;
-  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));
+    if (ctx->dsm_gather_balanced) {  // opt-in (amb_dsm_set_balanced_gather): strips handed out by candidate count
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      dsm_gather_kernel_bal<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+    } else {
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+    }
+    ctx->dsm_launches += 1;
+    AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));
 
-  CellArgs ca;
-  ca.G = G;
-  ca.order = ctx->point_order.as<unsigned int>();
-  ca.rec = rec;
-  ca.elevation = ga.elevation;
-  ca.cell_list = ga.cell_list;
-  ca.counters = counters;
-  ca.dbg_count = ga.dbg_count;
-  ca.dbg_level = ga.dbg_level;
-  dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(plan, ca);
-  ctx->dsm_launches += 1;
-  AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
-  AMB_CUDA(ctx, cudaGetLastError());
-  st = mirror_layer(ctx, out_layer);  // the result starts streaming to its host mirror (if one is registered)
-  if (st != AMB_OK) return st;
+    CellArgs ca;
+    ca.G = G;
+    ca.order = ctx->point_order.as<unsigned int>();
+    ca.rec = rec;
+    ca.elevation = ga.elevation;
+    ca.cell_list = ga.cell_list;
+    ca.counters = counters;
+    ca.dbg_count = ga.dbg_count;
+    ca.dbg_level = ga.dbg_level;
+    dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(plan, ca);
+    ctx->dsm_launches += 1;
+    AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
+    AMB_CUDA(ctx, cudaGetLastError());
+    st = mirror_layer(ctx, out_layer);  // the result starts streaming to its host mirror (if one is registered)
+    if (st != AMB_OK) return st;
+  }
   ctx->dsm_debug_valid = ctx->dsm_debug;
   ctx->last_dsm_plan.assign(reinterpret_cast<const unsigned char*>(&plan),
                             reinterpret_cast<const unsigned char*>(&plan) + sizeof(plan));

@@ -179,6 +179,10 @@ int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell);
  * candidates, so that the lanes of a warp finish together (a warp otherwise waits for the slowest of 32 Poisson-distributed
  * strips).  Same output bits: every cell is still summed by one thread in canonical order. */
 int amb_dsm_set_balanced_gather(amb_ctx* ctx, int enable);
+/* Opt-in (default 1 = off): with a host mirror registered for the output layer (amb_set_host_mirror), evaluate the map's
+ * tile columns in `chunks` groups and start each group's download as soon as it is final, so that the layer's trip to the
+ * host overlaps the evaluation of the remaining groups.  Same launches restricted to tile-column ranges: same output bits. */
+int amb_dsm_set_stream_chunks(amb_ctx* ctx, int chunks);
 /* The y-interval (y_lo, y_hi] covered by the cells of columns [col_begin, col_end) (points are assigned to the
  * rank whose interval holds y - center_easting), and how far a point can act across a stripe border. */
 int amb_stripe_y_interval(const amb_geometry* geom, int32_t col_begin, int32_t col_end, double* y_lo, double* y_hi);

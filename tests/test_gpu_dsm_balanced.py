@@ -83,3 +83,27 @@ def test_lane_utilisation_improves_at_the_benchmark_density(monkeypatch):
         wm, _ = counter((name + "_warp_max").encode())
         util[name] = it / (32.0 * wm)
     assert 0.7 < util["gather"] < 0.88 and util["gather_bal"] > 0.92
+
+
+# ---- amb_dsm_set_stream_chunks: gather + fill in tile-column groups, each group's columns mirrored to the host at once ----
+@pytest.mark.parametrize("chunks,col_range", [(4, None), (3, (20, 110)), (64, None), (2, (33, 64))])
+def test_chunked_evaluation_with_early_mirroring_gives_the_same_bits(monkeypatch, chunks, col_range):
+    rows, cols, res = 100, 140, 0.5
+    xyz = synth.point_cloud(28000, rows * res / 2 + 2.0, cols * res / 2 + 2.0, 77, holes=3, hole_sides=(3.0, 9.0))
+    monkeypatch.delenv("AMB_DSM_STREAM_CHUNKS", raising=False)
+    ref, _ = gpu_dsm(rows, cols, res, xyz, col_range=col_range)
+    assert np.isnan(ref["elevation"]).any()
+    for balanced in ("0", "1"):
+        monkeypatch.setenv("AMB_DSM_BALANCED_GATHER", balanced)
+        monkeypatch.setenv("AMB_DSM_STREAM_CHUNKS", str(chunks))
+        gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res), pinned=True).getMutable()
+        gm.to_device(0, col_range=col_range, names=("elevation",))
+        gm.set_mirrors(("elevation",))
+        d = amb.Dsm(amb.DsmSettings(), gm)
+        assert d.stream_chunks == chunks
+        for _ in range(2):      # the second round's writers must wait for the first round's chunk copies
+            amb.check(amb.lib().amb_init_layers(gm.context()), gm.context())
+            d.process(xyz, gm)
+            gm.sync()
+            c0, c1 = col_range if col_range else (0, cols)
+            assert np.array_equal(gm["elevation"][:, c0:c1].view(np.uint32), ref["elevation"][:, c0:c1].view(np.uint32))
