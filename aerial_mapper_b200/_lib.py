@@ -70,6 +70,7 @@ SYMBOLS = {
     "amb_download_layer": (C.c_int, [_P, C.c_int, _P]),
     "amb_download_layer_async": (C.c_int, [_P, C.c_int, _P]),
     "amb_set_host_mirror": (C.c_int, [_P, C.c_int, _P]),
+    "amb_set_host_mirror_compact": (C.c_int, [_P, C.c_int, C.c_int]),
     "amb_layer_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "amb_dsm_process": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double]),
     "amb_dsm_process_device": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double]),

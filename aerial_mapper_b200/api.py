@@ -161,10 +161,14 @@ class GridMap(object):
         """Register the host layers as mirrors (amb_set_host_mirror): process() streams every result layer back as
         soon as it is final, overlapping later stages; sync() completes the copies.  Use pinned layers."""
         ctx = self.context()
+        # opt-in one-byte transport of `ortho` / `observation_index` (amb_set_host_mirror_compact)
+        compact = os.environ.get("AMB_COMPACT_MIRRORS", "0") not in ("", "0")
         for name in names:
             slab = self._slab(name)
             ptr = slab.ctypes.data_as(C.c_void_p) if enable else None
             check(lib().amb_set_host_mirror(ctx, LAYER_ID[name], ptr), ctx)
+            if name in ("ortho", "observation_index"):
+                check(lib().amb_set_host_mirror_compact(ctx, LAYER_ID[name], 1 if (enable and compact) else 0), ctx)
 
     def to_device(self, device=0, col_range=None, names=HOT_LAYERS):
         """Make the layers device-resident (uploads the current host values once)."""

@@ -56,6 +56,7 @@ int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1) {
 
 int mirror_layer(amb_ctx* ctx, int layer) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer]) return AMB_OK;
+  if (ctx->compact[layer].enabled) return mirror_layer_compact(ctx, layer);  // opt-in (amb_set_host_mirror_compact)
   return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
 }
 
@@ -186,6 +187,7 @@ void amb_destroy(amb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  release_compact_mirrors(ctx);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layers[l]) cudaFree(ctx->layers[l]);
   DeviceBuffer* bufs[] = {&ctx->points,  &ctx->intensities, &ctx->records, &ctx->point_order,
@@ -213,6 +215,7 @@ int amb_sync(amb_ctx* ctx) {
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  join_compact_mirrors(ctx);  // host threads widening one-byte codes into the mirrors (opt-in; none otherwise)
   for (int l = 0; l < AMB_NUM_LAYERS; ++l) ctx->layer_copy_pending[l] = false;
   // Deferred reference CHECKs of the asynchronous `_device` entry points.
   if (ctx->counters.ptr) {

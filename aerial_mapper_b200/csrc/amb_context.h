@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/aerial_mapper_b200.h"
@@ -90,6 +91,18 @@ enum EventId {
   EV_COUNT
 };
 
+// Narrow transport of a small-integer result layer to its host mirror (mirror_compact.cu)
+struct CompactMirror {
+  bool enabled = false;
+  bool failed = false;
+  DeviceBuffer codes;                 // one byte per slab cell
+  uint8_t* host_codes = nullptr;      // pinned landing zone of the codes
+  size_t host_bytes = 0;
+  unsigned int* host_flag = nullptr;  // pinned + mapped: set by the pack kernel when a value has no code
+  std::vector<cudaEvent_t> chunk_events;
+  std::vector<std::thread> workers;   // expander threads of the round in flight
+};
+
 }  // namespace amb
 
 struct amb_ctx {
@@ -104,6 +117,7 @@ struct amb_ctx {
   cudaEvent_t stage_event = nullptr;    // last use of `stage` by an asynchronous copy
   unsigned int* host_flags = nullptr;   // pinned: device flags read back at the end of a host entry point
   float* host_mirror[AMB_NUM_LAYERS] = {};  // pinned host slabs that receive a layer as soon as it is final
+  amb::CompactMirror compact[AMB_NUM_LAYERS];  // opt-in one-byte transport (amb_set_host_mirror_compact)
   cudaEvent_t layer_copy_event[AMB_NUM_LAYERS] = {};  // completion of an asynchronous download of that layer
   bool layer_copy_pending[AMB_NUM_LAYERS] = {};
   bool dsm_timed = false, ortho_timed = false, dsm_had_h2d = false, ortho_had_h2d = false;
@@ -165,7 +179,11 @@ int ensure_layer(amb_ctx* ctx, int layer);
 int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for its pending asynchronous download
 int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab);  // on the copy stream, after current work
 int mirror_layer(amb_ctx* ctx, int layer);
-int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1);  // slab-local column range     // enqueue_layer_download to the registered host mirror, if any
+int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1);  // slab-local column range
+// mirror_compact.cu
+int mirror_layer_compact(amb_ctx* ctx, int layer);
+void join_compact_mirrors(amb_ctx* ctx);
+void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the registered host mirror, if any
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,

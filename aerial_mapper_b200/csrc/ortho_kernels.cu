@@ -386,8 +386,12 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   }
 
   AMB_CUDA(ctx, ctx->frame_table.reserve(n * sizeof(uint8_t*)));
+  const bool fresh_counters = ctx->counters.ptr == nullptr;
   AMB_CUDA(ctx, ctx->counters.reserve(64));
   unsigned int* counters = ctx->counters.as<unsigned int>();
+  // amb_sync reads the DSM's flags from the same block: a block this call allocates (no DSM ran on the context yet) must
+  // not hand it uninitialised device memory
+  if (fresh_counters) AMB_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, s));
   AMB_CUDA(ctx, cudaMemsetAsync(counters + 8, 0, 4, s));
   if (!select_only) {
     const uint8_t** table = ctx->stage.take<const uint8_t*>(n);

@@ -365,7 +365,8 @@ def run_ours(args):
                       "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W) / 1e9),
                       "ortho_dominance_cull": bool(getattr(ortho, "dominance_cull", False)),    # opt-in (AMB_ORTHO_DOMINANCE=1)
                       "dsm_balanced_gather": bool(getattr(dsm, "balanced_gather", False)),
-                      "dsm_stream_chunks": int(getattr(dsm, "stream_chunks", 1))},     # opt-in (AMB_DSM_STREAM_CHUNKS=K)     # opt-in (AMB_DSM_BALANCED_GATHER=1)
+                      "dsm_stream_chunks": int(getattr(dsm, "stream_chunks", 1)),      # opt-in (AMB_DSM_STREAM_CHUNKS=K)
+                      "compact_mirrors": os.environ.get("AMB_COMPACT_MIRRORS", "0") not in ("", "0")},  # opt-in, e2e only     # opt-in (AMB_DSM_BALANCED_GATHER=1)
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if e2e is not None:
         out["e2e"] = e2e

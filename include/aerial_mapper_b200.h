@@ -150,6 +150,12 @@ int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab);
  * uploaded; the ortho layer after the texel gather), on a second stream.  amb_sync() completes the copies.  This is
  * the host-authoritative model of the reference (process() mutates the caller's map) without serialising PCIe. */
 int amb_set_host_mirror(amb_ctx* ctx, int layer, float* host_slab);
+/* Opt-in narrow transport for the mirrors of AMB_LAYER_ORTHO and AMB_LAYER_OBSERVATION_INDEX (others:
+ * AMB_ERR_INVALID_ARGUMENT): the layer crosses PCIe as one byte per cell and host threads inside the library widen it to
+ * the float32 values of the mirror (amb_sync waits for them).  Whenever a value has no one-byte code — anything but the
+ * integers 0..255 (`ortho`) / 0..254 and the canonical NaN (`observation_index`) — the layer travels as float32 as before:
+ * the mirror always receives the layer's exact bits. */
+int amb_set_host_mirror_compact(amb_ctx* ctx, int layer, int enable);
 /* Device pointer of a layer slab (allocating it if needed), for device-side consumers (NCCL all-gather of
  * finished stripes, downstream kernels). */
 int amb_layer_device_ptr(amb_ctx* ctx, int layer, float** device_slab);

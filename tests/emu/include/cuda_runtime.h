@@ -101,9 +101,12 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
   *v = 148;
   return cudaSuccess;
 }
+// Fresh "device" and pinned memory is POISONED (0xA5...): code that relies on cudaMalloc returning zeros — it often
+// does on a real GPU, by accident — shows up here.
 template <typename T>
 inline cudaError_t cudaMalloc(T** p, size_t bytes) {
   *p = static_cast<T*>(std::malloc(bytes ? bytes : 1));
+  if (*p) std::memset(*p, 0xA5, bytes ? bytes : 1);
   return *p ? cudaSuccess : cudaErrorInvalidValue;
 }
 inline cudaError_t cudaFree(void* p) {
@@ -113,6 +116,7 @@ inline cudaError_t cudaFree(void* p) {
 template <typename T>
 inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) {
   *p = static_cast<T*>(std::malloc(bytes ? bytes : 1));
+  if (*p) std::memset(*p, 0xA5, bytes ? bytes : 1);
   return *p ? cudaSuccess : cudaErrorInvalidValue;
 }
 inline cudaError_t cudaFreeHost(void* p) {
@@ -214,6 +218,11 @@ inline double __longlong_as_double(long long v) {
 inline long long __double_as_longlong(double d) {
   long long v;
   std::memcpy(&v, &d, 8);
+  return v;
+}
+inline unsigned int __float_as_uint(float f) {
+  unsigned int v;
+  std::memcpy(&v, &f, 4);
   return v;
 }
 inline float __uint_as_float(unsigned int v) {

@@ -35,8 +35,8 @@ def run_child(marker, files, extra=(), sched=None):
 def test_pending_gpu_tests_pass_on_the_emulated_kernels(sched):
     # also with the block's threads scheduled in reverse and in a fresh pseudo-random order every round: a kernel whose
     # result depended on who runs first (e.g. a missing barrier between a write and another thread's read) would differ
-    tail = run_child("gpu_pending", ["test_gpu_ortho_dominance.py", "test_gpu_dsm_balanced.py", "test_ortho_from_pcl.py",
-                                     "test_stereo_rectify.py"], sched=sched)
+    tail = run_child("gpu_pending", ["test_gpu_ortho_dominance.py", "test_gpu_dsm_balanced.py", "test_gpu_compact_mirrors.py",
+                                     "test_ortho_from_pcl.py", "test_stereo_rectify.py"], sched=sched)
     assert " passed" in tail and "failed" not in tail
 
 
