@@ -16,11 +16,15 @@ import pytest
 from common import ROOT
 
 
-def run_child(marker, files, extra=(), sched=None):
+OPT_IN = ("AMB_ORTHO_DOMINANCE", "AMB_DSM_BALANCED_GATHER", "AMB_DSM_STREAM_CHUNKS", "AMB_COMPACT_MIRRORS")
+
+
+def run_child(marker, files, extra=(), sched=None, opt_in=None):
     env = dict(os.environ, AMB_TEST_EMU="1")
-    env.pop("AMB_ORTHO_DOMINANCE", None)
-    env.pop("AMB_DSM_BALANCED_GATHER", None)
-    env.pop("AMB_EMU_SCHED", None)
+    for k in OPT_IN + ("AMB_EMU_SCHED",):
+        env.pop(k, None)
+    if opt_in:
+        env.update(opt_in)
     if sched:
         env["AMB_EMU_SCHED"] = sched   # order in which the threads of a block take their turns (tests/emu/emu_runtime.cc)
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", marker, "-p", "no:cacheprovider"] + list(extra) + \
@@ -48,6 +52,17 @@ def test_validated_gpu_tests_pass_on_the_emulated_kernels_too():
     assert " passed" in tail and "failed" not in tail
     import re
     assert int(re.search(r"(\d+) passed", tail).group(1)) >= 50
+
+
+def test_validated_gpu_tests_with_every_opt_in_variant_switched_on():
+    # the configuration the next round is expected to make the default: dominance cull + balanced gather + chunked DSM
+    # with early mirroring + one-byte mirrors, all at once, against the same oracle-backed GPU tests
+    tail = run_child("gpu or gpu_pending", ["test_gpu_compact_mirrors.py", "test_gpu_ortho.py", "test_gpu_dsm.py",
+                                            "test_gpu_refsrc.py", "test_gpu_smoke.py"],
+                     extra=["-k", "not large and not full_baseline_size"],
+                     opt_in={"AMB_ORTHO_DOMINANCE": "1", "AMB_DSM_BALANCED_GATHER": "1", "AMB_DSM_STREAM_CHUNKS": "4",
+                             "AMB_COMPACT_MIRRORS": "1"})
+    assert " passed" in tail and "failed" not in tail
 
 
 @pytest.mark.parametrize("tool,seed,cases", [("emu_fuzz_dsm.py", 11, 6), ("emu_fuzz_ortho.py", 12, 8)])
