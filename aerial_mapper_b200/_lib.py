@@ -78,7 +78,6 @@ SYMBOLS = {
     "amb_dsm_set_density_hint": (C.c_int, [_P, C.c_double]),
     "amb_stripe_y_interval": (C.c_int, [C.POINTER(Geometry), C.c_int32, C.c_int32, C.POINTER(C.c_double),
                                         C.POINTER(C.c_double)]),
-    "amb_dsm_set_balanced_gather": (C.c_int, [_P, C.c_int]),
     "amb_dsm_set_stream_chunks": (C.c_int, [_P, C.c_int]),
     "amb_dsm_halo_reach": (C.c_double, [C.POINTER(Geometry), C.c_int32]),
     "amb_dsm_extract_halo": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, _P,

@@ -41,6 +41,12 @@ int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab) {
 int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer] || col1 <= col0)
     return AMB_OK;
+  if (ctx->compact[layer].enabled) {
+    // column chunks always travel as float32; expander threads of an earlier compact round may still be writing the mirror
+    for (std::thread& t : ctx->compact[layer].workers)
+      if (t.joinable()) t.join();
+    ctx->compact[layer].workers.clear();
+  }
   const size_t off = static_cast<size_t>(ctx->geom.rows) * static_cast<size_t>(col0);
   const size_t cnt = static_cast<size_t>(ctx->geom.rows) * static_cast<size_t>(col1 - col0);
   AMB_CUDA(ctx, cudaEventRecord(ctx->copy_done[0], ctx->stream));
@@ -58,6 +64,13 @@ int mirror_layer(amb_ctx* ctx, int layer) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer]) return AMB_OK;
   if (ctx->compact[layer].enabled) return mirror_layer_compact(ctx, layer);  // opt-in (amb_set_host_mirror_compact)
   return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
+}
+
+int ensure_counters(amb_ctx* ctx) {
+  if (ctx->counters.ptr) return AMB_OK;
+  AMB_CUDA(ctx, ctx->counters.reserve(CTR_COUNT * sizeof(unsigned int)));
+  AMB_CUDA(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, CTR_COUNT * sizeof(unsigned int), ctx->stream));
+  return AMB_OK;
 }
 
 int ensure_layer(amb_ctx* ctx, int layer) {
@@ -91,7 +104,10 @@ static int finish_flags(amb_ctx* ctx, unsigned int offset_words, int err_code) {
   ctx->host_flags[0] = 0;
   flag_to_host_kernel<<<1, 1, 0, ctx->stream>>>(ctx->counters.as<unsigned int>() + offset_words, mapped);
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ctx->host_flags[0] ? err_code : AMB_OK;
+  if (!ctx->host_flags[0]) return AMB_OK;
+  // reported: the sticky flag is cleared (ordered before any later kernel on the stream)
+  AMB_CUDA(ctx, cudaMemsetAsync(ctx->counters.as<unsigned int>() + offset_words, 0, sizeof(unsigned int), ctx->stream));
+  return err_code;
 }
 
 }  // namespace amb
@@ -215,14 +231,20 @@ int amb_sync(amb_ctx* ctx) {
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-  join_compact_mirrors(ctx);  // host threads widening one-byte codes into the mirrors (opt-in; none otherwise)
+  const int compact_status = join_compact_mirrors(ctx);  // host threads widening one-byte codes (opt-in; none otherwise)
   for (int l = 0; l < AMB_NUM_LAYERS; ++l) ctx->layer_copy_pending[l] = false;
+  if (compact_status != AMB_OK) return compact_status;
   // Deferred reference CHECKs of the asynchronous `_device` entry points.
   if (ctx->counters.ptr) {
-    unsigned int c[16];
+    unsigned int c[CTR_COUNT];
     AMB_CUDA(ctx, cudaMemcpy(c, ctx->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
-    if (c[1]) return AMB_ERR_COINCIDENT_POINT;
-    if (c[8]) return AMB_ERR_CHECK_FAILED;
+    if (c[CTR_DSM_COINCIDENT] || c[CTR_ORTHO_CHECK]) {  // reported once, then cleared (both streams are idle here)
+      unsigned int* d = ctx->counters.as<unsigned int>();
+      AMB_CUDA(ctx, cudaMemset(d + CTR_DSM_COINCIDENT, 0, sizeof(unsigned int)));
+      AMB_CUDA(ctx, cudaMemset(d + CTR_ORTHO_CHECK, 0, sizeof(unsigned int)));
+    }
+    if (c[CTR_DSM_COINCIDENT]) return AMB_ERR_COINCIDENT_POINT;
+    if (c[CTR_ORTHO_CHECK]) return AMB_ERR_CHECK_FAILED;
   }
   return AMB_OK;
 }
@@ -378,12 +400,6 @@ int amb_dsm_set_stream_chunks(amb_ctx* ctx, int chunks) {
   return AMB_OK;
 }
 
-int amb_dsm_set_balanced_gather(amb_ctx* ctx, int enable) {
-  if (!ctx) return AMB_ERR_INVALID_ARGUMENT;
-  ctx->dsm_gather_balanced = enable != 0;
-  return AMB_OK;
-}
-
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell) {
   if (!ctx || !(points_per_cell >= 0.0)) return AMB_ERR_INVALID_ARGUMENT;
   ctx->dsm_density_hint = points_per_cell;
@@ -431,7 +447,7 @@ int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpola
   int st = dsm_run(ctx, ctx->points.as<double>(), nullptr, n, interpolation_radius, center_easting, center_northing);
   ctx->dsm_timed = (st == AMB_OK);
   if (st != AMB_OK) return st;
-  return finish_flags(ctx, 1, AMB_ERR_COINCIDENT_POINT);
+  return finish_flags(ctx, CTR_DSM_COINCIDENT, AMB_ERR_COINCIDENT_POINT);
 }
 
 int amb_dsm_enable_debug(amb_ctx* ctx, int enable) {
@@ -496,7 +512,7 @@ int amb_ortho_process(amb_ctx* ctx, const amb_camera* camera, const double* T_G_
   if (st != AMB_OK) return st;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_END], ctx->stream));
   ctx->ortho_timed = true;
-  return finish_flags(ctx, 8, AMB_ERR_CHECK_FAILED);
+  return finish_flags(ctx, CTR_ORTHO_CHECK, AMB_ERR_CHECK_FAILED);
 }
 
 int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force) {
@@ -532,12 +548,12 @@ int amb_get_timings(amb_ctx* ctx, amb_timings* out) {
     out->dsm_fill_ms = ms(EV_DSM_GATHER_END, EV_DSM_FILL_END);
     out->dsm_total_ms = ms(EV_DSM_BEGIN, EV_DSM_FILL_END);
     out->dsm_kernel_launches = ctx->dsm_launches;
-    unsigned int c[4] = {0, 0, 0, 0};
+    unsigned int c[CTR_COUNT] = {};
     if (ctx->counters.ptr) {
       AMB_CUDA(ctx, cudaMemcpy(c, ctx->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
     }
-    out->dsm_cells_empty = c[0];
-    out->dsm_points_binned = c[2];
+    out->dsm_cells_empty = static_cast<int64_t>(c[CTR_DSM_LIST]) + c[CTR_DSM_LIST_DONE];
+    out->dsm_points_binned = c[CTR_DSM_BINNED];
   }
   if (ctx->ortho_timed) {
     if (ctx->ortho_two_phase) {  // select kernel | sub-rectangle copies | texel kernel

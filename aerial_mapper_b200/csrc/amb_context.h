@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -91,10 +92,27 @@ enum EventId {
   EV_COUNT
 };
 
+// Slots of the small device flag/counter block (amb_ctx::counters, 16 x uint32).  Every stage resets only its own slots.
+// The two deferred reference-CHECK flags are STICKY: kernels set them, the next amb_sync() or host entry point reports
+// and clears them — an asynchronous `_device` sequence (ortho -> dsm -> amb_sync) cannot lose an earlier call's failure.
+enum CounterSlot {
+  CTR_DSM_LIST = 0,        // length of the warp-per-cell list (reset per DSM launch group)
+  CTR_DSM_COINCIDENT = 1,  // sticky: CHECK(distances[i] > 0.0), dsm.cc:165
+  CTR_DSM_BINNED = 2,      // points the binning kept
+  CTR_DSM_DENSE = 3,       // tiles handed whole to the warp-per-cell kernel
+  CTR_DSM_LIST_DONE = 5,   // chunked evaluation: list lengths of the chunks already evaluated
+  CTR_DSM_AMBIGUOUS = 4,   // f32 gather: cells re-evaluated exactly because a pair fell inside the guard band
+  CTR_ORTHO_CHECK = 8,     // sticky: CHECK(alpha > 0.0), ortho-backward-grid.cc:178
+  CTR_PCL_CELLS = 10,      // adaptive OrthoFromPcl: cells listed for the 10^k radius growth
+  CTR_PCL_UNRESOLVED = 11, // adaptive OrthoFromPcl: cells no level could fill
+  CTR_COUNT = 16
+};
+
 // Narrow transport of a small-integer result layer to its host mirror (mirror_compact.cu)
 struct CompactMirror {
   bool enabled = false;
-  bool failed = false;
+  std::atomic<bool> failed{false};    // an expander thread could not wait for its chunk: reported by amb_sync, which then
+                                      // re-downloads the layer as float32
   DeviceBuffer codes;                 // one byte per slab cell
   uint8_t* host_codes = nullptr;      // pinned landing zone of the codes
   size_t host_bytes = 0;
@@ -134,13 +152,12 @@ struct amb_ctx {
   amb::DeviceBuffer bin_starts;   // uint32 G[nb + 2]
   amb::DeviceBuffer block_sums;   // scan spine
   amb::DeviceBuffer empty_cells;  // uint32 list of cells that need the expanding-radius pass
-  amb::DeviceBuffer counters;     // small: [0] empty count, [1] error flag, [2] binned points (2 x uint32)
+  amb::DeviceBuffer counters;     // small flag/counter block, see amb::CounterSlot
   amb::DeviceBuffer dbg_count;    // int32 per slab cell
   amb::DeviceBuffer dbg_level;    // int8 per slab cell
   double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
   int dsm_stream_chunks = 1;  // opt-in (> 1): gather + fill in column chunks, each chunk's result mirrored to the host at once
-  bool dsm_gather_balanced = false;  // opt-in: dsm_gather_kernel_bal (strips handed to threads by candidate count)
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;
   std::vector<unsigned char> last_dsm_plan;  // the DsmPlan of the last dsm_run (read by the adaptive OrthoFromPcl pass)
@@ -155,7 +172,7 @@ struct amb_ctx {
   int64_t ortho_h2d_bytes = 0;
   bool ortho_two_phase = false;
   bool ortho_brute_force = false;
-  bool ortho_dominance = false;  // opt-in per-tile dominance cull of the frame list (ortho_kernel<.., DOM = true>)
+  bool ortho_dominance = true;   // per-tile dominance cull of the frame list (ortho_kernel_dom); amb_ortho_set_dominance_cull(0) = plain list
 
   size_t slab_cells() const { return static_cast<size_t>(geom.rows) * static_cast<size_t>(col_end - col_begin); }
 };
@@ -175,6 +192,7 @@ inline int fail(amb_ctx* ctx, cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return amb::fail(ctx, e__, #call); \
   } while (0)
 
+int ensure_counters(amb_ctx* ctx);  // allocates (zeroed) the flag/counter block on first use
 int ensure_layer(amb_ctx* ctx, int layer);
 int wait_layer_copy(amb_ctx* ctx, int layer);  // writers of a layer wait for its pending asynchronous download
 int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab);  // on the copy stream, after current work
@@ -182,7 +200,7 @@ int mirror_layer(amb_ctx* ctx, int layer);
 int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1);  // slab-local column range
 // mirror_compact.cu
 int mirror_layer_compact(amb_ctx* ctx, int layer);
-void join_compact_mirrors(amb_ctx* ctx);
+int join_compact_mirrors(amb_ctx* ctx);         // AMB_ERR_CUDA if an expander failed (the layer was re-downloaded as float32)
 void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the registered host mirror, if any
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) dsm_count_kernel(const double* __restrict
   }
   // total binned points (stats only): warp-aggregate, one atomic per warp
   for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counters[2], local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counters[CTR_DSM_BINNED], local);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -319,35 +319,14 @@ struct GatherArgs {
   const PointRec* rec;
   float* elevation;
   unsigned int* cell_list;  // cells handed to the warp-per-cell kernel
-  unsigned int* counters;   // [0] list length, [1] coincident-point flag, [3] dense tiles
+  unsigned int* counters;   // amb::CounterSlot
   int* dbg_count;
   signed char* dbg_level;
   int capacity;  // points that fit the shared-memory stage
   int tiles_i;
 };
 
-#define AMB_GATHER_BALANCED 0
-#define AMB_GATHER_STRIP gather_strip
-#define AMB_GATHER_KERNEL dsm_gather_kernel
-#define AMB_GATHER_STRIP_ID_PARAM
-#define AMB_GATHER_LANE ti
 #include "dsm_gather_body.inc"
-#undef AMB_GATHER_BALANCED
-#undef AMB_GATHER_STRIP
-#undef AMB_GATHER_KERNEL
-#undef AMB_GATHER_STRIP_ID_PARAM
-#undef AMB_GATHER_LANE
-#define AMB_GATHER_BALANCED 1
-#define AMB_GATHER_STRIP gather_strip_bal
-#define AMB_GATHER_KERNEL dsm_gather_kernel_bal
-#define AMB_GATHER_STRIP_ID_PARAM , int strip_id
-#define AMB_GATHER_LANE lane
-#include "dsm_gather_body.inc"
-#undef AMB_GATHER_BALANCED
-#undef AMB_GATHER_STRIP
-#undef AMB_GATHER_KERNEL
-#undef AMB_GATHER_STRIP_ID_PARAM
-#undef AMB_GATHER_LANE
 
 // ---------------------------------------------------------------------------------------------------------------
 // K5: one warp per listed cell.  Evaluates the reference's complete per-cell sequence (primary query, then the
@@ -366,7 +345,7 @@ struct CellArgs {
 
 __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ DsmPlan plan, const CellArgs args) {
   const int lane = threadIdx.x & 31;
-  const unsigned int n_cells = args.counters[0];
+  const unsigned int n_cells = args.counters[CTR_DSM_LIST];
   const unsigned int warps_total = gridDim.x * (blockDim.x >> 5);
   const int P = plan.P;
   for (unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n_cells; c += warps_total) {
@@ -455,7 +434,7 @@ __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ D
     }
     coincident = __any_sync(0xffffffffu, coincident);
     if (lane == 0) {
-      if (coincident && plan.mode == 0) atomicExch(&args.counters[1], 1u);
+      if (coincident && plan.mode == 0) atomicExch(&args.counters[CTR_DSM_COINCIDENT], 1u);
       // OrthoFromPcl perfect match: numerator = that height, denominator = 1 (ortho-from-pcl.cc:90-96)
       const double value = (coincident && plan.mode == 1) ? match_z : __ddiv_rn(num, den);
       args.elevation[cell] = __double2float_rn(value);
@@ -465,6 +444,12 @@ __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ D
       }
     }
   }
+}
+
+// chunked evaluation: the list of the chunk just evaluated is done; keep its length for amb_get_timings
+__global__ void roll_list_counter_kernel(unsigned int* counters) {
+  counters[CTR_DSM_LIST_DONE] += counters[CTR_DSM_LIST];
+  counters[CTR_DSM_LIST] = 0;
 }
 
 // Half-width (in bins along i) of the window that can hold a point with d2 < thr, for a bin row |dj| away.
@@ -624,7 +609,8 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   AMB_CUDA(ctx, ctx->records.reserve(n * sizeof(PointRec)));
   AMB_CUDA(ctx, ctx->point_order.reserve(n * sizeof(unsigned int)));
   AMB_CUDA(ctx, ctx->empty_cells.reserve(cells * sizeof(unsigned int)));
-  AMB_CUDA(ctx, ctx->counters.reserve(64));
+  st = ensure_counters(ctx);
+  if (st != AMB_OK) return st;
   if (ctx->dsm_debug) {
     AMB_CUDA(ctx, ctx->dbg_count.reserve(cells * sizeof(int)));
     AMB_CUDA(ctx, ctx->dbg_level.reserve(cells));
@@ -635,7 +621,9 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   PointRec* rec = ctx->records.as<PointRec>();
 
   AMB_CUDA(ctx, cudaMemsetAsync(G, 0, g_elems * sizeof(unsigned int), s));
-  AMB_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, s));
+  // only this stage's own slots: the sticky CHECK flags of earlier asynchronous calls stay until they are reported
+  AMB_CUDA(ctx, cudaMemsetAsync(counters + CTR_DSM_LIST, 0, sizeof(unsigned int), s));
+  AMB_CUDA(ctx, cudaMemsetAsync(counters + CTR_DSM_BINNED, 0, 4 * sizeof(unsigned int), s));  // [2..5]
   if (ctx->dsm_debug) {
     AMB_CUDA(ctx, cudaMemsetAsync(ctx->dbg_count.ptr, 0xff, cells * sizeof(int), s));
     AMB_CUDA(ctx, cudaMemsetAsync(ctx->dbg_level.ptr, 0xff, cells, s));
@@ -687,15 +675,12 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   // groups — gather + warp-per-cell fill per group — and each group's finished columns start travelling to the host
   // at once, so the download of the layer overlaps the evaluation of the remaining groups.  The launches of a group are
   // the un-chunked ones restricted to its tile columns (plan.tile_j0 and the grid size), so every result is unchanged.
-  const int chunks = (ctx->dsm_stream_chunks > 1 && ctx->host_mirror[out_layer]) ? std::min(ctx->dsm_stream_chunks, tiles_j) : 1;
+  // (Dsm only: OrthoFromPcl's adaptive pass rewrites the layer afterwards, so its columns are not final per chunk)
+  const int chunks = (mode == 0 && ctx->dsm_stream_chunks > 1 && ctx->host_mirror[out_layer])
+                         ? std::min(ctx->dsm_stream_chunks, tiles_j) : 1;
   if (chunks > 1) {
-    if (ctx->dsm_gather_balanced) {
-      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    } else {
-      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    }
+    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
     CellArgs ca;
     ca.G = G;
     ca.order = ctx->point_order.as<unsigned int>();
@@ -711,12 +696,8 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
       if (tj1 <= tj0) continue;
       DsmPlan pc = plan;
       pc.tile_j0 = plan.tile_j0 + tj0;
-      if (c > 0) AMB_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(unsigned int), s));  // the cell list restarts
-      if (ctx->dsm_gather_balanced) {
-        dsm_gather_kernel_bal<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
-      } else {
-        dsm_gather_kernel<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
-      }
+      if (c > 0) roll_list_counter_kernel<<<1, 1, 0, s>>>(counters);  // the cell list restarts; its length is kept
+      dsm_gather_kernel<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
       dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(pc, ca);
       ctx->dsm_launches += 2;
       // slab-local columns of this group's tiles (tiles are aligned to GLOBAL columns)
@@ -729,15 +710,9 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
     AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
     AMB_CUDA(ctx, cudaGetLastError());
   } else {
-    if (ctx->dsm_gather_balanced) {  // opt-in (amb_dsm_set_balanced_gather): strips handed out by candidate count
-      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-      dsm_gather_kernel_bal<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
-    } else {
-      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-      dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
-    }
+    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
     ctx->dsm_launches += 1;
     AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));
 

@@ -12,6 +12,7 @@
 //   chunked D2H         of the codes on the copy stream, one event per chunk
 //   expander threads    wait for their chunks' events and write the float32 values into the caller's mirror
 // amb_sync (and a later compact mirror of the same layer) join the threads.
+#include <exception>
 #include <thread>
 
 #include "amb_context.h"
@@ -82,18 +83,33 @@ void expand_chunks(amb_ctx* ctx, int layer, int first, int stride, int n_chunks,
 
 }  // namespace
 
-void join_compact_mirrors(amb_ctx* ctx) {
+static void join_layer(CompactMirror& cm) {
+  for (std::thread& t : cm.workers)
+    if (t.joinable()) t.join();
+  cm.workers.clear();
+}
+
+int join_compact_mirrors(amb_ctx* ctx) {
+  int status = AMB_OK;
   for (int l = 0; l < AMB_NUM_LAYERS; ++l) {
-    for (std::thread& t : ctx->compact[l].workers)
-      if (t.joinable()) t.join();
-    ctx->compact[l].workers.clear();
+    CompactMirror& cm = ctx->compact[l];
+    join_layer(cm);
+    if (cm.failed.exchange(false)) {
+      // an expander gave up (its chunk event could not be waited for): the mirror is only partly widened.  Repair it with
+      // a plain synchronous float32 download and tell the caller.
+      status = AMB_ERR_CUDA;
+      ctx->last_error = "compact mirror: an expander thread failed; layer re-downloaded as float32";
+      if (ctx->host_mirror[l] && ctx->layers[l])
+        cudaMemcpy(ctx->host_mirror[l], ctx->layers[l], ctx->slab_cells() * sizeof(float), cudaMemcpyDeviceToHost);
+    }
   }
+  return status;
 }
 
 void release_compact_mirrors(amb_ctx* ctx) {
-  join_compact_mirrors(ctx);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l) {
     CompactMirror& cm = ctx->compact[l];
+    join_layer(cm);
     cm.codes.release();
     if (cm.host_codes) cudaFreeHost(cm.host_codes);
     if (cm.host_flag) cudaFreeHost(cm.host_flag);
@@ -111,9 +127,7 @@ int mirror_layer_compact(amb_ctx* ctx, int layer) {
   CompactMirror& cm = ctx->compact[layer];
   const int nan_code = layer == AMB_LAYER_OBSERVATION_INDEX ? 255 : -1;
   const size_t cells = ctx->slab_cells();
-  for (std::thread& t : cm.workers)  // the previous round's expansion of this layer
-    if (t.joinable()) t.join();
-  cm.workers.clear();
+  join_layer(cm);  // the previous round's expansion of this layer
   AMB_CUDA(ctx, cm.codes.reserve(cells));
   if (cm.host_bytes < cells) {
     if (cm.host_codes) cudaFreeHost(cm.host_codes);
@@ -130,7 +144,7 @@ int mirror_layer_compact(amb_ctx* ctx, int layer) {
   pack_codes_kernel<<<kNumSMsB200 * 8, 256, 0, ctx->stream>>>(d_layer, d_codes, cells, nan_code, d_flag);
   AMB_CUDA(ctx, cudaGetLastError());
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the flag decides the transport (the layer is final here)
-  if (*cm.host_flag || cm.failed) {
+  if (*cm.host_flag || cm.failed.load()) {
     // not representable (e.g. `ortho` written by OrthoFromPcl, or uploaded by the caller): plain float32 transport
     return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
   }
@@ -147,8 +161,13 @@ int mirror_layer_compact(amb_ctx* ctx, int layer) {
     AMB_CUDA(ctx, cudaEventRecord(cm.chunk_events[c], ctx->copy_stream));
   }
   const int n_workers = n_chunks < kExpanders ? n_chunks : kExpanders;
-  for (int t = 0; t < n_workers; ++t)
-    cm.workers.emplace_back(expand_chunks, ctx, layer, t, n_workers, n_chunks, cells, nan_code);
+  try {
+    for (int t = 0; t < n_workers; ++t)
+      cm.workers.emplace_back(expand_chunks, ctx, layer, t, n_workers, n_chunks, cells, nan_code);
+  } catch (const std::exception&) {  // thread creation failed: nothing may escape the extern "C" boundary
+    join_layer(cm);
+    return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);  // overwrites whatever the started workers wrote
+  }
   return AMB_OK;
 }
 

@@ -386,13 +386,11 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   }
 
   AMB_CUDA(ctx, ctx->frame_table.reserve(n * sizeof(uint8_t*)));
-  const bool fresh_counters = ctx->counters.ptr == nullptr;
-  AMB_CUDA(ctx, ctx->counters.reserve(64));
+  {
+    const int cst = ensure_counters(ctx);  // born zeroed; the CHECK(alpha > 0) flag is sticky until reported
+    if (cst != AMB_OK) return cst;
+  }
   unsigned int* counters = ctx->counters.as<unsigned int>();
-  // amb_sync reads the DSM's flags from the same block: a block this call allocates (no DSM ran on the context yet) must
-  // not hand it uninitialised device memory
-  if (fresh_counters) AMB_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, s));
-  AMB_CUDA(ctx, cudaMemsetAsync(counters + 8, 0, 4, s));
   if (!select_only) {
     const uint8_t** table = ctx->stage.take<const uint8_t*>(n);
     for (size_t f = 0; f < n; ++f) table[f] = d_images[f];
@@ -407,7 +405,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   a.elevation_angle = ctx->layers[AMB_LAYER_ELEVATION_ANGLE];
   a.observation_index = ctx->layers[AMB_LAYER_OBSERVATION_INDEX];
   a.out_layer = ctx->layers[out_layer];
-  a.error_flag = counters + 8;
+  a.error_flag = counters + CTR_ORTHO_CHECK;
   int* bbox = nullptr;      // pinned: initial values up, results back
   int* bbox_back = nullptr;
   const size_t cells = ctx->slab_cells();

@@ -198,14 +198,14 @@ int pcl_adaptive_finish(amb_ctx* ctx, int pass_status, size_t n, int32_t interpo
   DsmPlan plan;
   std::memcpy(&plan, ctx->last_dsm_plan.data(), sizeof(plan));
 
-  unsigned int* counters = ctx->counters.as<unsigned int>();  // [2] = points the binning kept; [8], [9] used here
+  unsigned int* counters = ctx->counters.as<unsigned int>();  // see amb::CounterSlot
   unsigned int h_counters[16];
   if (cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
       cudaStreamSynchronize(s) != cudaSuccess) {
     cudaGetLastError();
     return restore(AMB_ERR_CUDA);
   }
-  if (static_cast<size_t>(h_counters[2]) != n) {
+  if (static_cast<size_t>(h_counters[CTR_DSM_BINNED]) != n) {
     ctx->last_error = "adaptive interpolation needs every point inside the map's bin grid (map + apron)";
     return restore(AMB_ERR_UNSUPPORTED);
   }
@@ -217,8 +217,8 @@ int pcl_adaptive_finish(amb_ctx* ctx, int pass_status, size_t n, int32_t interpo
   a.rec = ctx->records.as<PointRec>();
   a.ortho = ortho;
   a.cell_list = ctx->empty_cells.as<unsigned int>();
-  a.n_cells = counters + 8;
-  a.unresolved = counters + 9;
+  a.n_cells = counters + CTR_PCL_CELLS;
+  a.unresolved = counters + CTR_PCL_UNRESOLVED;
   // thresholds (double)(lambda * interpolation_radius), lambda = 10, 100, ... in `int` (ortho-from-pcl.cc:64-70)
   long long lambda = 10;
   const double slack = 1e-6;
@@ -233,12 +233,12 @@ int pcl_adaptive_finish(amb_ctx* ctx, int pass_status, size_t n, int32_t interpo
   }
 
   wait_layer_copy(ctx, AMB_LAYER_ORTHO);  // the regular pass may have started mirroring the layer to the host
-  if (cudaMemsetAsync(counters + 8, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) {
+  if (cudaMemsetAsync(counters + CTR_PCL_CELLS, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) {
     cudaGetLastError();
     return restore(AMB_ERR_CUDA);
   }
   pcl_adaptive_list_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(ortho, cells, ctx->empty_cells.as<unsigned int>(),
-                                                            counters + 8);
+                                                            counters + CTR_PCL_CELLS);
   pcl_adaptive_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(plan, a);
   ctx->dsm_launches += 2;
   if (cudaGetLastError() != cudaSuccess ||
@@ -247,11 +247,11 @@ int pcl_adaptive_finish(amb_ctx* ctx, int pass_status, size_t n, int32_t interpo
     cudaGetLastError();
     return restore(AMB_ERR_CUDA);
   }
-  if (h_counters[9]) {
+  if (h_counters[CTR_PCL_UNRESOLVED]) {
     ctx->last_error = "adaptive interpolation: no neighbour within 10^k * radius <= INT_MAX (undefined in the reference)";
     return restore(AMB_ERR_UNSUPPORTED);
   }
-  ctx->last_cells_empty = static_cast<int64_t>(h_counters[8]);
+  ctx->last_cells_empty = static_cast<int64_t>(h_counters[CTR_PCL_CELLS]);
   cudaFree(saved);
   return mirror_layer(ctx, AMB_LAYER_ORTHO);  // the final layer (re)starts streaming to its host mirror
 }

@@ -181,10 +181,6 @@ int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t
  * rank passes the same global figure to keep all summation orders — every output bit — independent of the
  * sharding.  0 (default): derive it from the points passed to each call. */
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell);
-/* Opt-in (default 0): the gather kernel hands its 1x4-cell strips to threads in order of their number of staged
- * candidates, so that the lanes of a warp finish together (a warp otherwise waits for the slowest of 32 Poisson-distributed
- * strips).  Same output bits: every cell is still summed by one thread in canonical order. */
-int amb_dsm_set_balanced_gather(amb_ctx* ctx, int enable);
 /* Opt-in (default 1 = off): with a host mirror registered for the output layer (amb_set_host_mirror), evaluate the map's
  * tile columns in `chunks` groups and start each group's download as soon as it is final, so that the layer's trip to the
  * host overlaps the evaluation of the remaining groups.  Same launches restricted to tile-column ranges: same output bits. */
@@ -284,7 +280,7 @@ int amb_ortho_process_device(amb_ctx* ctx, const amb_camera* camera, const doubl
 /* 0 = cull frames per tile with the conservative view-cone test (default), 1 = brute force over all frames
  * (the cull's own correctness reference). */
 int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force);
-/* Opt-in (default 0): per-tile DOMINANCE cull of the frame list.  A frame whose largest
+/* Default 1 (0 = plain conservative list): per-tile DOMINANCE cull of the frame list.  A frame whose largest
  * possible observation angle over the tile is smaller — by a margin far above float32 rounding — than the smallest
  * possible one of a frame that sees every landmark of the tile can never end up as the winner of the reference's
  * running-maximum recurrence (ortho-backward-grid.cc:173-183) nor change who does, so it is not evaluated: same output

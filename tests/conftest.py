@@ -10,9 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with `pytest -m gpu` on the B200 box)")
-    config.addinivalue_line("markers", "gpu_pending: needs a CUDA device and has NOT yet run on one (written after the "
-                            "round's GPU budget was spent); first thing to run next round: `pytest -m gpu_pending`, "
-                            "then promote to `gpu`")
 
 
 EMULATED = os.environ.get("AMB_TEST_EMU", "0") not in ("", "0")
@@ -58,7 +55,7 @@ def pytest_collection_modifyitems(config, items):
     # are skipped so that an accidental plain `pytest` on the CPU container stays green.
     n = None
     for item in items:
-        if "gpu" in item.keywords or "gpu_pending" in item.keywords:
+        if "gpu" in item.keywords:
             if n is None:
                 n = _gpu_count()
             if n == 0 and not os.environ.get("AMB_REQUIRE_GPU"):

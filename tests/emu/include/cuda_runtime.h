@@ -152,6 +152,10 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
   std::memset(d, v, n);
   return cudaSuccess;
 }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) {
+  std::memset(d, v, n);
+  return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
   *s = std::malloc(1);
   return cudaSuccess;

@@ -2,10 +2,9 @@
 CUDA runtime (tests/emu/README.md — test infrastructure only, never a fallback of the product) and driven through the
 normal Python mirror + C ABI by the GPU tests themselves, in a child pytest process with AMB_TEST_EMU=1.
 
-  * every `gpu_pending` test (kernels written after the round's GPU budget was spent: the orthomosaic's dominance cull,
-    the DSM's load-balanced gather, OrthoFromPcl's adaptive interpolation, the stereo rectification maps), and
-  * the already validated `gpu` tests (all but the few that create inputs with torch.cuda): the emulation reproduces
-    what the B200 produced — and re-checks, on every CPU run, the CURRENT sources' kernel and host logic.
+  * the `gpu` tests (all but the few that create inputs with torch.cuda): the emulation reproduces what the B200
+    produced — and re-checks, on every CPU run, the CURRENT sources' kernel and host logic, also under reversed and
+    pseudo-random thread scheduling orders.
 This does not replace a GPU run (fibers run one after the other: no races, no memory model, no performance)."""
 import os
 import subprocess
@@ -16,7 +15,7 @@ import pytest
 from common import ROOT
 
 
-OPT_IN = ("AMB_ORTHO_DOMINANCE", "AMB_DSM_BALANCED_GATHER", "AMB_DSM_STREAM_CHUNKS", "AMB_COMPACT_MIRRORS")
+OPT_IN = ("AMB_ORTHO_DOMINANCE", "AMB_DSM_STREAM_CHUNKS", "AMB_COMPACT_MIRRORS", "AMB_DSM_PRECISION")
 
 
 def run_child(marker, files, extra=(), sched=None, opt_in=None):
@@ -36,11 +35,11 @@ def run_child(marker, files, extra=(), sched=None, opt_in=None):
 
 
 @pytest.mark.parametrize("sched", [None, "reverse", "random:5"])
-def test_pending_gpu_tests_pass_on_the_emulated_kernels(sched):
+def test_variant_gpu_tests_pass_on_the_emulated_kernels(sched):
     # also with the block's threads scheduled in reverse and in a fresh pseudo-random order every round: a kernel whose
     # result depended on who runs first (e.g. a missing barrier between a write and another thread's read) would differ
-    tail = run_child("gpu_pending", ["test_gpu_ortho_dominance.py", "test_gpu_dsm_balanced.py", "test_gpu_compact_mirrors.py",
-                                     "test_ortho_from_pcl.py", "test_stereo_rectify.py"], sched=sched)
+    tail = run_child("gpu", ["test_gpu_ortho_dominance.py", "test_gpu_compact_mirrors.py", "test_ortho_from_pcl.py",
+                             "test_stereo_rectify.py"], sched=sched)
     assert " passed" in tail and "failed" not in tail
 
 
@@ -55,13 +54,11 @@ def test_validated_gpu_tests_pass_on_the_emulated_kernels_too():
 
 
 def test_validated_gpu_tests_with_every_opt_in_variant_switched_on():
-    # the configuration the next round is expected to make the default: dominance cull + balanced gather + chunked DSM
-    # with early mirroring + one-byte mirrors, all at once, against the same oracle-backed GPU tests
-    tail = run_child("gpu or gpu_pending", ["test_gpu_compact_mirrors.py", "test_gpu_ortho.py", "test_gpu_dsm.py",
-                                            "test_gpu_refsrc.py", "test_gpu_smoke.py"],
+    # chunked DSM with early mirroring + one-byte mirrors, both at once, against the same oracle-backed GPU tests
+    tail = run_child("gpu", ["test_gpu_compact_mirrors.py", "test_gpu_ortho.py", "test_gpu_dsm.py",
+                             "test_gpu_refsrc.py", "test_gpu_smoke.py"],
                      extra=["-k", "not large and not full_baseline_size"],
-                     opt_in={"AMB_ORTHO_DOMINANCE": "1", "AMB_DSM_BALANCED_GATHER": "1", "AMB_DSM_STREAM_CHUNKS": "4",
-                             "AMB_COMPACT_MIRRORS": "1"})
+                     opt_in={"AMB_DSM_STREAM_CHUNKS": "4", "AMB_COMPACT_MIRRORS": "1"})
     assert " passed" in tail and "failed" not in tail
 
 

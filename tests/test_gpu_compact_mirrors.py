@@ -1,9 +1,7 @@
 """Opt-in one-byte transport of `ortho` / `observation_index` to their host mirrors (amb_set_host_mirror_compact,
 csrc/mirror_compact.cu): the mirror must receive exactly the bits of the layer — through the codes when every value has
 one, through the plain float32 download otherwise.
-
-`gpu_pending`: written after the round's GPU budget was spent; green on the CPU emulation of the sources (tests/emu);
-not yet run on a B200 (where it is also a PCIe-traffic optimisation to be measured: 0.2 GB instead of 0.8 GB per step)."""
+"""
 import numpy as np
 import pytest
 
@@ -11,7 +9,7 @@ import aerial_mapper_b200 as amb
 from aerial_mapper_b200 import synth
 from test_gpu_ortho import make_inputs
 
-pytestmark = pytest.mark.gpu_pending
+pytestmark = pytest.mark.gpu
 
 NAMES = ("ortho", "elevation", "elevation_angle", "observation_index")
 

@@ -94,6 +94,24 @@ def test_map_offset_and_center_shift():
     assert_parity(gm, dbg, *oracle_dsm(110, 70, 0.5, xyz, 1, **kw))
 
 
+def test_non_finite_heights_only_touch_the_cells_they_reach():
+    # the reference keeps z = +-inf / NaN points (its loader only requires z > -100): they poison exactly the cells whose
+    # ball contains them — a point out of reach must leave a cell's sums untouched (round-1 advisor finding)
+    xyz = synth.point_cloud(4000, 34.0, 34.0, seed=23)
+    xyz[7, 2] = np.inf
+    xyz[1234, 2] = -np.inf
+    xyz[2500, 2] = np.nan
+    gm, dbg = gpu_dsm(64, 64, 1.0, xyz)
+    e, cnt, lvl = oracle_dsm(64, 64, 1.0, xyz)
+    ge = gm["elevation"]
+    assert np.array_equal(dbg[1], lvl)
+    assert np.array_equal(np.isnan(ge), np.isnan(e)) and np.array_equal(np.isinf(ge), np.isinf(e))
+    fin = np.isfinite(e)
+    assert fin.sum() > 3000 and (~fin).sum() >= 3
+    assert np.array_equal(np.sign(ge[~fin & ~np.isnan(e)]), np.sign(e[~fin & ~np.isnan(e)]))
+    assert ulp_diff(ge[fin], e[fin]).max() <= 1
+
+
 def test_points_outside_the_map_still_count():
     # the reference's kd-tree holds every point: points beyond the border contribute to edge cells
     xyz = synth.point_cloud(8000, 30.0, 30.0, seed=15)   # map is 40 x 40 m, cloud 60 x 60 m

@@ -3,9 +3,7 @@ compact rectification on the host, then the per-pixel fill of the four CV_32FC1 
 CPU: the oracle restatement against numpy linear algebra and the geometric properties rectification must have
 (common rows, positive disparity), and the product's host half (plain C++ inside the CUDA library, runs without a
 GPU) bit for bit against the oracle.  GPU: the map-fill kernel against the oracle, bit-identical floats.
-
-NB: the GPU test carries the `gpu_pending` marker — it was written after the round's GPU budget was spent and has
-not yet run on a B200."""
+"""
 import numpy as np
 import pytest
 
@@ -119,7 +117,7 @@ def test_map_fill_fails_loudly_without_a_gpu(gpu_count):
     assert ei.value.status == _lib.AMB_ERR_NO_DEVICE
 
 
-@pytest.mark.gpu_pending
+@pytest.mark.gpu
 @pytest.mark.parametrize("w,h,seed", [(640, 480, 2), (333, 77, 3), (4000, 3000, 4), (5, 3, 5)])
 def test_gpu_maps_bit_identical_to_the_oracle(w, h, seed):
     K, R1, R2, t1, t2 = rig(seed, w, h)

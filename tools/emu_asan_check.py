@@ -1,6 +1,6 @@
 """Memory-safety pass over the kernel source: the emulated library (tests/emu) rebuilt with AddressSanitizer — global
 ("device") buffers are heap blocks, static and dynamic shared memory are globals / heap with red zones — and driven through
-random DSM (plain + balanced), orthomosaic (plain + dominance), adaptive OrthoFromPcl and rectification workloads.
+random DSM, orthomosaic (plain + dominance), adaptive OrthoFromPcl and rectification workloads.
 
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
         python tools/emu_asan_check.py
@@ -32,11 +32,9 @@ for case in range(6):
     res = float(rng.choice([0.25, 0.5, 1.0])); radius = int(rng.choice([1, 2, 3]))
     n = max(1, int(rng.choice([0.3, 2.0, 30.0]) * rows * res * cols * res))
     xyz = np.c_[rng.uniform(-rows*res/2-3, rows*res/2+3, n), rng.uniform(-cols*res/2-3, cols*res/2+3, n), rng.normal(100, 5, n)]
-    for bal in ("0", "1"):
-        os.environ["AMB_DSM_BALANCED_GATHER"] = bal
-        gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
-        d = amb.Dsm(amb.DsmSettings(interpolation_radius=radius), gm); d.debug = True
-        d.process(xyz, gm)
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+    d = amb.Dsm(amb.DsmSettings(interpolation_radius=radius), gm); d.debug = True
+    d.process(xyz, gm)
     camd = synth.scaled_camera(0.05)
     poses = synth.lawnmower_poses(2, 3, rows * res / 2, cols * res / 2, 50.0, int(rng.integers(0, 99)), jitter_pos=0.5)
     imgs = [synth.procedural_image(k, camd["width"], camd["height"]) for k in range(len(poses))]
