@@ -26,6 +26,7 @@ LAYER_NAMES = ("ortho", "elevation", "elevation_angle", "num_observations", "ele
 LAYER_ID = {name: k for k, name in enumerate(LAYER_NAMES)}
 
 DIST_NONE, DIST_RADTAN, DIST_EQUIDISTANT = 0, 1, 2
+DSM_F64, DSM_F32 = 0, 1
 
 
 class Geometry(C.Structure):
@@ -79,6 +80,7 @@ SYMBOLS = {
     "amb_stripe_y_interval": (C.c_int, [C.POINTER(Geometry), C.c_int32, C.c_int32, C.POINTER(C.c_double),
                                         C.POINTER(C.c_double)]),
     "amb_dsm_set_stream_chunks": (C.c_int, [_P, C.c_int]),
+    "amb_dsm_set_precision": (C.c_int, [_P, C.c_int]),
     "amb_dsm_halo_reach": (C.c_double, [C.POINTER(Geometry), C.c_int32]),
     "amb_dsm_extract_halo": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, _P,
                                        _P, C.c_uint32, _P]),
@@ -116,7 +118,7 @@ def build(force=False, verbose=False):
         need = any(os.path.getmtime(s) > t for s in srcs)
     if need:
         out = None if verbose else subprocess.DEVNULL
-        subprocess.check_call(["make", "-C", CSRC, "-B", "all"], stdout=out)
+        subprocess.check_call(["make", "-C", CSRC, "-j", "8", "all"], stdout=out)
     return LIB_PATH
 
 

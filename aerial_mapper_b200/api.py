@@ -251,6 +251,10 @@ class Dsm(object):
         self.settings_ = settings
         self.debug = False
         self.last_debug = None
+        # arithmetic of the gather's weights and sums (amb_dsm_set_precision): None = the library default ("f32":
+        # float32 weights and sums, neighbour sets exact; the environment variable AMB_DSM_PRECISION=f64|f32, read by
+        # the library itself, overrides that default process-wide — how the tests run both), or "f32" / "f64"
+        self.precision = None
         # opt-in chunked evaluation + early mirroring of finished columns (amb_dsm_set_stream_chunks); 1 = off
         self.stream_chunks = max(1, int(os.environ.get("AMB_DSM_STREAM_CHUNKS", "1") or 1))
 
@@ -269,6 +273,8 @@ class Dsm(object):
             map.upload(("elevation",))
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
         check(lib().amb_dsm_set_stream_chunks(ctx, int(self.stream_chunks)), ctx)
+        if self.precision is not None:
+            check(lib().amb_dsm_set_precision(ctx, _lib.DSM_F32 if self.precision == "f32" else _lib.DSM_F64), ctx)
         check(lib().amb_dsm_process(ctx, pc.ctypes.data_as(C.c_void_p), n, int(s.interpolation_radius),
                                     float(s.center_easting), float(s.center_northing)), ctx)
         self._fetch_debug(map)
@@ -285,6 +291,8 @@ class Dsm(object):
         s = self.settings_
         check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
         check(lib().amb_dsm_set_stream_chunks(ctx, int(self.stream_chunks)), ctx)
+        if self.precision is not None:
+            check(lib().amb_dsm_set_precision(ctx, _lib.DSM_F32 if self.precision == "f32" else _lib.DSM_F64), ctx)
         if d_ids is None:
             check(lib().amb_dsm_process_device(ctx, C.c_void_p(int(d_xyz)), int(n), int(s.interpolation_radius),
                                                float(s.center_easting), float(s.center_northing)), ctx)

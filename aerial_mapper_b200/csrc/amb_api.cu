@@ -1,5 +1,6 @@
 // amb_api.cu — the extern "C" boundary (include/aerial_mapper_b200.h): context, layers, host entry points.
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <new>
 
@@ -185,6 +186,12 @@ int amb_create(const amb_geometry* geom, int device, int32_t col_begin, int32_t 
   ctx->device = device;
   ctx->col_begin = col_begin;
   ctx->col_end = col_end;
+  // process-wide override of the gather's default arithmetic (amb_dsm_set_precision still wins per context): lets the
+  // same test suite / demo binary run in either mode without code changes
+  if (const char* p = std::getenv("AMB_DSM_PRECISION")) {
+    if (p[0] == 'f' && p[1] == '6') ctx->dsm_precision = AMB_DSM_F64;
+    if (p[0] == 'f' && p[1] == '3') ctx->dsm_precision = AMB_DSM_F32;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -400,6 +407,12 @@ int amb_dsm_set_stream_chunks(amb_ctx* ctx, int chunks) {
   return AMB_OK;
 }
 
+int amb_dsm_set_precision(amb_ctx* ctx, int precision) {
+  if (!ctx || (precision != AMB_DSM_F64 && precision != AMB_DSM_F32)) return AMB_ERR_INVALID_ARGUMENT;
+  ctx->dsm_precision = precision;
+  return AMB_OK;
+}
+
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell) {
   if (!ctx || !(points_per_cell >= 0.0)) return AMB_ERR_INVALID_ARGUMENT;
   ctx->dsm_density_hint = points_per_cell;
@@ -420,7 +433,12 @@ double amb_dsm_halo_reach(const amb_geometry* g, int32_t interpolation_radius) {
   const std::vector<double> thr = dsm_thresholds(interpolation_radius);
   double m = 0.0;
   for (double t : thr) m = std::max(m, t);
-  return std::sqrt(m) + g->resolution;  // largest retry reach + one cell of slack
+  // (i) the largest retry threshold's reach + one cell of slack: what a border CELL can see; (ii) everything a border
+  // TILE stages — tiles are aligned to global columns, so a tile cut by the stripe border extends up to tile-width - 1
+  // columns beyond it, plus the window apron: with those points present every tile of the stripe stages exactly the
+  // point set it stages in the undivided map, so tile-level quantities (shared-memory / warp-per-cell decision, the FP32
+  // gather's height offset) are independent of the sharding.
+  return std::max(std::sqrt(m) + g->resolution, dsm_tile_reach_cells(g->resolution, interpolation_radius) * g->resolution);
 }
 
 int amb_dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n, double y_lo, double y_hi,

@@ -158,6 +158,7 @@ struct amb_ctx {
   double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
   int dsm_stream_chunks = 1;  // opt-in (> 1): gather + fill in column chunks, each chunk's result mirrored to the host at once
+  int dsm_precision = AMB_DSM_F32;  // amb_dsm_set_precision: arithmetic of the tile gather's weights and sums
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;
   std::vector<unsigned char> last_dsm_plan;  // the DsmPlan of the last dsm_run (read by the adaptive OrthoFromPcl pass)
@@ -216,5 +217,6 @@ int pcl_adaptive_finish(amb_ctx* ctx, int pass_status, size_t n, int32_t interpo
 int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const uint8_t* const* d_images,
               const uint8_t* const* h_images, size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
 std::vector<double> dsm_thresholds(int32_t interpolation_radius);
+double dsm_tile_reach_cells(double resolution, int32_t interpolation_radius);  // tile width + window apron + 1, in cells
 
 }  // namespace amb

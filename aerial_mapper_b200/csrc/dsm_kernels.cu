@@ -32,6 +32,7 @@
 // by the order of the double-precision summation and by z*(1/d2) replacing z/d2 (both O(1e-16) relative).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "amb_context.h"
 #include "dsm_plan.h"
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t t0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t0 < n; t0 += stride * kBatch) {
     double px[kBatch], py[kBatch], pz[kBatch];
-    unsigned int bucket[kBatch], pos[kBatch];
+    unsigned int bucket[kBatch], pos[kBatch], code[kBatch];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const size_t t = t0 + u * stride;
@@ -229,9 +230,12 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
       py[u] -= plan.shift_y;
       int bi, bj;
       bucket[u] = 0xffffffffu;
-      if (fine_bin(plan, px[u], py[u], &bi, &bj))
+      code[u] = 0u;
+      if (fine_bin(plan, px[u], py[u], &bi, &bj)) {
         bucket[u] = static_cast<unsigned int>(bi >> plan.Bshift) +
                     static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
+        code[u] = (static_cast<unsigned int>(bi) << 4) | (static_cast<unsigned int>(bj) & 15u);  // PointRec::idx, high word
+      }
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
@@ -242,7 +246,8 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
         // the canonical-order key: position in the caller's array, or the caller's own (global) point id when the
         // cloud arrives sharded — so that a stripe sees the same order as the undivided map
         const size_t t = t0 + u * stride;
-        store_rec(rec + pos[u], px[u], py[u], pz[u], ids ? ids[t] : static_cast<unsigned long long>(t));
+        const unsigned long long id = ids ? (ids[t] & 0xffffffffull) : static_cast<unsigned long long>(t);
+        store_rec(rec + pos[u], px[u], py[u], pz[u], id | (static_cast<unsigned long long>(code[u]) << 32));
       }
   }
 }
@@ -303,9 +308,9 @@ __global__ void __launch_bounds__(256) dsm_bucket_order_kernel(const unsigned in
     } else {
       // far denser than the bucket size was chosen for: rank against the keys in global memory
       for (unsigned int q = lane; q < k; q += 32) {
-        const unsigned long long mine = __ldg(&rec[s + q].idx);
+        const unsigned int mine = rec_id(__ldg(&rec[s + q].idx));
         unsigned int rank = 0;
-        for (unsigned int o = 0; o < k; ++o) rank += __ldg(&rec[s + o].idx) < mine ? 1u : 0u;
+        for (unsigned int o = 0; o < k; ++o) rank += rec_id(__ldg(&rec[s + o].idx)) < mine ? 1u : 0u;
         order[s + rank] = s + q;
       }
     }
@@ -327,6 +332,7 @@ struct GatherArgs {
 };
 
 #include "dsm_gather_body.inc"
+#include "dsm_gather_f32.inc"
 
 // ---------------------------------------------------------------------------------------------------------------
 // K5: one warp per listed cell.  Evaluates the reference's complete per-cell sequence (primary query, then the
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(256) dsm_cell_kernel(const __grid_constant__ D
             den += w;
           } else {
             coincident = true;
-            const unsigned long long id = __ldg(&pr->idx);
+            const unsigned long long id = rec_id(__ldg(&pr->idx));
             if (id < match_idx) {
               match_idx = id;
               match_z = pz;
@@ -451,6 +457,16 @@ __global__ void roll_list_counter_kernel(unsigned int* counters) {
   counters[CTR_DSM_LIST_DONE] += counters[CTR_DSM_LIST];
   counters[CTR_DSM_LIST] = 0;
 }
+
+}  // namespace
+
+double dsm_tile_reach_cells(double resolution, int32_t interpolation_radius) {
+  const double slack = 1e-6;
+  const int W = static_cast<int>(std::floor(std::sqrt(static_cast<double>(interpolation_radius)) / resolution + 0.5 + slack));
+  return static_cast<double>(TJ + W + 1);
+}
+
+namespace {
 
 // Half-width (in bins along i) of the window that can hold a point with d2 < thr, for a bin row |dj| away.
 // A point binned to cell b lies within (0.5 + slack) cells of that cell's centre along each axis, so its
@@ -570,6 +586,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   plan.P = static_cast<int>(std::floor(std::sqrt(thr_max) / g.resolution + 0.5 + slack));
   plan.P = std::max(plan.P, plan.W);
   if (plan.P > kMaxHalfWidth) return AMB_ERR_UNSUPPORTED;  // resolution far finer than the search radius
+  if (g.rows >= (1 << 27)) return AMB_ERR_UNSUPPORTED;      // PointRec::idx keeps the fine bin row in 28 bits
   half_widths(plan.thr0, g.resolution, plan.W, plan.hw);
 
   // Bucket edge: a power of two (<= 16 cells) such that a bucket holds a few dozen points at the cloud's average
@@ -649,13 +666,36 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   const int max_runs = (NJw + B - 1) / B + 1;
   size_t off_bytes = (static_cast<size_t>(NIw) * NJw + 2 + kStrip + 2 * W + 2 * max_runs + 1) * 4;
   off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
-  const size_t per_point = 16 + 8 + 4;
+  // FP32 gather (the default; amb_dsm_set_precision): Dsm only — OrthoFromPcl keeps the all-FP64 kernel
+  const bool f32 = ctx->dsm_precision == AMB_DSM_F32 && mode == 0;
+  int f32_bps = 5;  // register-allocation target of the f32 gather (development knob: AMB_DSM_F32_BPS=4)
+  if (const char* e = std::getenv("AMB_DSM_F32_BPS")) f32_bps = e[0] == '4' ? 4 : 5;
+  // f32: record 16 + original index 4 + record position 4 + 2 raw-record bin ids 2 x 2 + bin id of the slot 2
+  const size_t per_point = f32 ? 16 + 4 + 4 + 2 * 2 + 2 : 16 + 8 + 4;
+  if (f32) {  // bins of 1 x kStrip cells (dsm_gather_f32.inc): a much smaller start table
+    const int NJb = (NJw + kStrip - 1) / kStrip;
+    off_bytes = (static_cast<size_t>(NIw) * NJb + 2 + (kStrip + 2 * W + kStrip - 1) / kStrip + 2 * max_runs + 1) * 4;
+    off_bytes = (off_bytes + 15) & ~static_cast<size_t>(15);
+  }
+  {
+    // Bound on |d2_f32 - d2| (dsm_gather_f32.inc): local coordinates |c| <= M are rounded to float (relative u = 2^-24),
+    // the difference adds one rounding, the two squares and the sum three more:
+    //   |d(dx)| <= 2uM + u|dx|,   |d(d2)| <= 2(|dx| + |dy|)(2uM + u sqrt(d2)) + 3u d2,   |dx| + |dy| <= sqrt(2 d2)
+    // evaluated at d2 = thr0 (+ the band itself) with a safety factor of 2.
+    const double u = 5.9604644775390625e-8;
+    const double M = (TI / 2 + plan.W + 2) * g.resolution;
+    const double t = plan.thr0 * 1.01;
+    const double bound = 2.0 * std::sqrt(2.0 * t) * (2.0 * u * M + u * std::sqrt(t)) + 3.0 * u * t;
+    plan.thr_f = static_cast<float>(plan.thr0);
+    plan.eps_f = static_cast<float>(2.0 * bound);
+    plan.zrange_limit = 4096.0;
+  }
   // Stage size: 1.6x the expected number of points in a tile window under a uniform density (the tail of a
   // Poisson count is far inside that; denser tiles go to the warp-per-cell kernel), clamped to [24 KB, 100 KB]
   // so that several blocks stay resident per SM (227 KB usable).
   if (off_bytes + per_point * 64 > 200 * 1024) return AMB_ERR_UNSUPPORTED;
   const double expect = per_cell * static_cast<double>(NIw) * static_cast<double>(NJw);
-  size_t smem = off_bytes + static_cast<size_t>(1.6 * expect + 64.0) * per_point;
+  size_t smem = off_bytes + static_cast<size_t>((f32 ? 1.4 : 1.6) * expect + 64.0) * per_point;
   smem = std::min<size_t>(std::max<size_t>(smem, 24 * 1024), 100 * 1024);
   smem = std::max(smem, off_bytes + per_point * 64);
   smem = (smem + 1023) & ~static_cast<size_t>(1023);
@@ -681,6 +721,10 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   if (chunks > 1) {
     AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
+    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_f32<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
     CellArgs ca;
     ca.G = G;
     ca.order = ctx->point_order.as<unsigned int>();
@@ -697,7 +741,13 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
       DsmPlan pc = plan;
       pc.tile_j0 = plan.tile_j0 + tj0;
       if (c > 0) roll_list_counter_kernel<<<1, 1, 0, s>>>(counters);  // the cell list restarts; its length is kept
-      dsm_gather_kernel<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
+      if (f32 && f32_bps == 4) {
+        dsm_gather_kernel_f32<4><<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
+      } else if (f32) {
+        dsm_gather_kernel_f32<5><<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
+      } else {
+        dsm_gather_kernel<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
+      }
       dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(pc, ca);
       ctx->dsm_launches += 2;
       // slab-local columns of this group's tiles (tiles are aligned to GLOBAL columns)
@@ -710,9 +760,19 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
     AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));
     AMB_CUDA(ctx, cudaGetLastError());
   } else {
-    AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+    if (f32 && f32_bps == 4) {
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      dsm_gather_kernel_f32<4><<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+    } else if (f32) {
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel_f32<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      dsm_gather_kernel_f32<5><<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+    } else {
+      AMB_CUDA(ctx, cudaFuncSetAttribute(dsm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      dsm_gather_kernel<<<ga.tiles_i * tiles_j, kGatherThreads, smem, s>>>(plan, ga);
+    }
     ctx->dsm_launches += 1;
     AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_GATHER_END], s));
 

@@ -13,8 +13,13 @@ constexpr int kMaxHalfWidth = 128;  // cells; window half-width limit (sqrt(thre
 
 struct PointRec {  // 32 bytes, one DRAM sector
   double x, y, z;
+  // low word: original index (or the caller's global point id, < 2^32) — the canonical-order key;
+  // high word: the point's fine bin as computed ONCE by the scatter kernel, (bi << 4) | (bj & 15), so that the tile
+  // gather bins its window with integer arithmetic only (bj's upper bits follow from the bucket row the record is in)
   unsigned long long idx;
 };
+__host__ __device__ inline unsigned int rec_id(unsigned long long idx_word) { return static_cast<unsigned int>(idx_word); }
+__host__ __device__ inline unsigned int rec_code(unsigned long long idx_word) { return static_cast<unsigned int>(idx_word >> 32); }
 
 struct DsmPlan {
   int rows, cols_slab, col_begin;
@@ -35,6 +40,10 @@ struct DsmPlan {
   int n_thr;
   double thr[kMaxThresholds];
   short hw[kMaxHalfWidth + 1];  // half-width along i of the primary window at |dj|
+  // FP32 gather (dsm_gather_f32.inc)
+  float thr_f;          // (float)thr0 — an int, exact
+  float eps_f;          // |d2_f32 - d2_reference| <= eps_f for every pair a tile can stage (see dsm_run)
+  double zrange_limit;  // tiles whose staged heights span more than this go to the all-FP64 kernel
 };
 
 __device__ __forceinline__ double cell_x(const DsmPlan& p, int i) {

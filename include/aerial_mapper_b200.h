@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 1
+#define AMB_ABI_VERSION 2
 
 typedef enum amb_status {
   AMB_OK = 0,
@@ -181,6 +181,14 @@ int amb_dsm_process_device_ids(amb_ctx* ctx, const double* d_xyz, const uint64_t
  * rank passes the same global figure to keep all summation orders — every output bit — independent of the
  * sharding.  0 (default): derive it from the points passed to each call. */
 int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell);
+/* Arithmetic of the tile gather's IDW weights and sums.  Neighbour SETS (d2 < threshold), retry levels and the NaN mask
+ * are the reference's exact double-precision decisions in both modes.
+ *   AMB_DSM_F32 (default): weights 1/d2 and both sums in float32 from tile-local coordinates and heights; any cell with a
+ *       (cell, point) pair too close to the decision boundary for float32 to decide is re-evaluated in double.  Heights
+ *       differ from the reference by far less than the 1e-4 relative the task allows (in practice <= 1 float32 ulp).
+ *   AMB_DSM_F64: everything in double in the reference's operation order (<= 1 float32 ulp by construction; ~2x slower). */
+typedef enum amb_dsm_precision { AMB_DSM_F64 = 0, AMB_DSM_F32 = 1 } amb_dsm_precision;
+int amb_dsm_set_precision(amb_ctx* ctx, int precision);
 /* Opt-in (default 1 = off): with a host mirror registered for the output layer (amb_set_host_mirror), evaluate the map's
  * tile columns in `chunks` groups and start each group's download as soon as it is final, so that the layer's trip to the
  * host overlaps the evaluation of the remaining groups.  Same launches restricted to tile-column ranges: same output bits. */

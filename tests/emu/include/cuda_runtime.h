@@ -45,6 +45,9 @@ struct dim3 {
 struct double2 {
   double x, y;
 };
+struct float2 {
+  float x, y;
+};
 struct float4 {
   float x, y, z, w;
 };
@@ -55,6 +58,11 @@ struct int2 {
   int x, y;
 };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+// packed FP32 pairs (sm_100 FADD2 / FFMA2): two independent IEEE operations
+inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 inline int2 make_int2(int x, int y) { return int2{x, y}; }

@@ -54,7 +54,7 @@ def test_header_compiles_as_c_and_cpp(tmp_path):
 
 def test_gpu_free_entry_points():
     L = amb.lib()
-    assert L.amb_abi_version() == 1
+    assert L.amb_abi_version() == 2
     assert b"coincide" in L.amb_status_string(-3)
     g = amb.Geometry()
     # setGeometry: size = round(length / resolution), length = size * resolution

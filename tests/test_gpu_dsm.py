@@ -1,8 +1,11 @@
 """GPU parity of the DSM path: the CUDA library through the C ABI (aerial_mapper_b200.Dsm = dsm::Dsm mirror)
 against the CPU oracle on the same seeded inputs, the golden fixture, and size-independent properties at scale.
 
-Bars: neighbour counts, retry-threshold indices and the NaN mask are integer-exact; elevation within 1e-6
-relative (north_star allows 1e-4) — and in fact expected bit-identical up to double summation order."""
+Bars: neighbour counts, retry-threshold indices and the NaN mask are integer-exact in BOTH arithmetic modes of the gather
+(amb_dsm_set_precision; the whole module runs once per mode, AMB_DSM_PRECISION):
+  f64  elevation <= 1 float32 ulp from the oracle (bit-identical up to double summation order)
+  f32  (library default) float32 weights / sums from tile-local coordinates: elevation within 1e-6 relative and <= 4 ulp
+       (north_star allows 1e-4 relative); measured: > 99.9 % of the cells bit-identical to the f64 mode."""
 import ctypes as C
 import os
 
@@ -17,6 +20,8 @@ from oracle import pyoracle as po
 pytestmark = pytest.mark.gpu
 
 REL = 1e-6
+PRECISION = os.environ.get("AMB_DSM_PRECISION", "f32").lower()
+MAX_ULP = 1 if PRECISION == "f64" else 4
 
 
 def gpu_dsm(rows, cols, res, xyz, radius=1, ce=0.0, cn=0.0, pos=(0.0, 0.0), elevation=None, col_range=None):
@@ -52,7 +57,7 @@ def assert_parity(gm, dbg, e, cnt, lvl):
     assert np.array_equal(np.isnan(ge), np.isnan(e))
     ok = ~np.isnan(e)
     assert np.allclose(ge[ok], e[ok], rtol=REL, atol=0.0)
-    assert ulp_diff(ge, e).max() <= 1
+    assert ulp_diff(ge, e).max() <= MAX_ULP
 
 
 CASES = [
@@ -84,7 +89,7 @@ def test_golden_fixture():
     t = gl >= 0
     assert np.array_equal(gc[t], z["neighbour_count"][t])
     assert np.array_equal(np.isnan(gm["elevation"]), np.isnan(z["elevation"]))
-    assert ulp_diff(gm["elevation"], z["elevation"]).max() <= 1
+    assert ulp_diff(gm["elevation"], z["elevation"]).max() <= MAX_ULP
 
 
 def test_map_offset_and_center_shift():
@@ -109,7 +114,7 @@ def test_non_finite_heights_only_touch_the_cells_they_reach():
     fin = np.isfinite(e)
     assert fin.sum() > 3000 and (~fin).sum() >= 3
     assert np.array_equal(np.sign(ge[~fin & ~np.isnan(e)]), np.sign(e[~fin & ~np.isnan(e)]))
-    assert ulp_diff(ge[fin], e[fin]).max() <= 1
+    assert ulp_diff(ge[fin], e[fin]).max() <= MAX_ULP
 
 
 def test_points_outside_the_map_still_count():
@@ -130,7 +135,7 @@ def test_repeated_process_keeps_untouched_cells():
     e, _, _ = oracle_dsm(80, 80, 0.5, a)
     e, _, _ = oracle_dsm(80, 80, 0.5, b, elevation=e)
     assert np.array_equal(np.isnan(gm["elevation"]), np.isnan(e))
-    assert ulp_diff(gm["elevation"], e).max() <= 1
+    assert ulp_diff(gm["elevation"], e).max() <= MAX_ULP
 
 
 def test_resident_map_matches_host_mode():
@@ -278,7 +283,7 @@ def test_sharded_cloud_with_border_halos_is_bit_identical_to_the_undivided_map(o
         gm.to_device(0, col_range=(c0, c1), names=("elevation",))
         y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
         m = sharding.owner_mask(xyz[:, 1], y_lo, y_hi, r, world)
-        hx = sharding.HaloExchange(torch, world, r, 20000, xyz[m], ids[m], dev)
+        hx = sharding.HaloExchange(torch, world, r, 60000, xyz[m], ids[m], dev)
         if on_library_stream:  # torch plumbing ordered on the context's own stream, no host syncs
             hx.use_stream(torch.cuda.ExternalStream(amb.lib().amb_stream(gm.context()), device=dev))
         reach = amb.lib().amb_dsm_halo_reach(ctypes_byref(gm.geometry), 1)
@@ -330,7 +335,9 @@ def test_property_full_baseline_size_c2():
     d.process_device(xyz.data_ptr(), n, gm)
     gm.sync()
     t = gm.timings()
-    assert t["dsm_points_binned"] == n and t["dsm_cells_empty"] == 0
+    assert t["dsm_points_binned"] == n
+    # warp-per-cell list: nothing at this density in f64 mode; in f32 mode only the cells with a pair inside the guard band
+    assert t["dsm_cells_empty"] == 0 if PRECISION == "f64" else t["dsm_cells_empty"] < 1e-3 * rows * cols
     gm.download(("elevation",))
     e = gm["elevation"]
     assert not np.isnan(e).any() and (e == np.float32(77.5)).all()
