@@ -84,6 +84,14 @@ SYMBOLS = {
     "amb_dsm_halo_reach": (C.c_double, [C.POINTER(Geometry), C.c_int32]),
     "amb_dsm_extract_halo": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, _P,
                                        _P, C.c_uint32, _P]),
+    "amb_comm_unique_id": (C.c_int, [_P]),
+    "amb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "amb_comm_destroy": (C.c_int, [_P]),
+    "amb_comm_size": (C.c_int, [_P]),
+    "amb_comm_rank": (C.c_int, [_P]),
+    "amb_dsm_process_sharded_device": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double,
+                                                 C.c_uint32]),
+    "amb_dsm_process_sharded": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double, C.c_uint32]),
     "amb_dsm_enable_debug": (C.c_int, [_P, C.c_int]),
     "amb_dsm_download_debug": (C.c_int, [_P, _P, _P]),
     "amb_dsm_thresholds": (C.c_int, [C.c_int32, _P, C.c_int32]),

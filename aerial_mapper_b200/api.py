@@ -301,6 +301,33 @@ class Dsm(object):
                                                    int(s.interpolation_radius), float(s.center_easting),
                                                    float(s.center_northing)), ctx)
 
+    def process_sharded_device(self, d_xyz, d_ids, n_local, map, halo_capacity):
+        """A cloud sharded by stripe, the exchange step included (amb_dsm_process_sharded_device): this rank's points
+        and global ids (device pointers) -> border halo compaction -> one NCCL all-gather inside the library -> the
+        stripe's elevation.  Collective over the communicator the map's context joined (sharding.init_comm);
+        asynchronous — map.sync() before reading results."""
+        ctx = map.context()
+        s = self.settings_
+        check(lib().amb_dsm_enable_debug(ctx, 1 if self.debug else 0), ctx)
+        if self.precision is not None:
+            check(lib().amb_dsm_set_precision(ctx, _lib.DSM_F32 if self.precision == "f32" else _lib.DSM_F64), ctx)
+        check(lib().amb_dsm_process_sharded_device(ctx, C.c_void_p(int(d_xyz)), C.c_void_p(int(d_ids)), int(n_local),
+                                                   int(s.interpolation_radius), float(s.center_easting),
+                                                   float(s.center_northing), int(halo_capacity)), ctx)
+
+    def process_sharded(self, point_cloud, ids, map, halo_capacity):
+        """Same with this rank's points (float64 [n, 3]) and global ids (uint64 [n]) in host memory."""
+        pc = np.ascontiguousarray(point_cloud, dtype=np.float64)
+        idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        n = pc.size // 3
+        ctx = map.context()
+        s = self.settings_
+        if self.precision is not None:
+            check(lib().amb_dsm_set_precision(ctx, _lib.DSM_F32 if self.precision == "f32" else _lib.DSM_F64), ctx)
+        check(lib().amb_dsm_process_sharded(ctx, pc.ctypes.data_as(C.c_void_p), idv.ctypes.data_as(C.c_void_p), n,
+                                            int(s.interpolation_radius), float(s.center_easting),
+                                            float(s.center_northing), int(halo_capacity)), ctx)
+
     def _fetch_debug(self, map):
         if not self.debug:
             self.last_debug = None

@@ -210,10 +210,13 @@ void amb_destroy(amb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  amb_comm_destroy(ctx);
+  ctx->halo_send.release();
+  ctx->halo_recv.release();
   release_compact_mirrors(ctx);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layers[l]) cudaFree(ctx->layers[l]);
-  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->intensities, &ctx->records, &ctx->point_order,
+  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->point_ids, &ctx->intensities, &ctx->records, &ctx->point_order,
                             &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
                           &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
                           &ctx->frame_cull, &ctx->frame_rects, &ctx->ortho_pix, &ctx->ortho_bbox};
@@ -245,10 +248,15 @@ int amb_sync(amb_ctx* ctx) {
   if (ctx->counters.ptr) {
     unsigned int c[CTR_COUNT];
     AMB_CUDA(ctx, cudaMemcpy(c, ctx->counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
-    if (c[CTR_DSM_COINCIDENT] || c[CTR_ORTHO_CHECK]) {  // reported once, then cleared (both streams are idle here)
+    if (c[CTR_DSM_COINCIDENT] || c[CTR_ORTHO_CHECK] || c[CTR_HALO_OVERFLOW]) {  // reported once, then cleared
       unsigned int* d = ctx->counters.as<unsigned int>();
       AMB_CUDA(ctx, cudaMemset(d + CTR_DSM_COINCIDENT, 0, sizeof(unsigned int)));
       AMB_CUDA(ctx, cudaMemset(d + CTR_ORTHO_CHECK, 0, sizeof(unsigned int)));
+      AMB_CUDA(ctx, cudaMemset(d + CTR_HALO_OVERFLOW, 0, sizeof(unsigned int)));
+    }
+    if (c[CTR_HALO_OVERFLOW]) {
+      ctx->last_error = "a rank's border halo exceeded halo_capacity (amb_dsm_process_sharded_device): result incomplete";
+      return AMB_ERR_SIZE_MISMATCH;
     }
     if (c[CTR_DSM_COINCIDENT]) return AMB_ERR_COINCIDENT_POINT;
     if (c[CTR_ORTHO_CHECK]) return AMB_ERR_CHECK_FAILED;

@@ -101,6 +101,7 @@ enum CounterSlot {
   CTR_DSM_BINNED = 2,      // points the binning kept
   CTR_DSM_DENSE = 3,       // tiles handed whole to the warp-per-cell kernel
   CTR_DSM_LIST_DONE = 5,   // chunked evaluation: list lengths of the chunks already evaluated
+  CTR_HALO_OVERFLOW = 6,   // sticky: a rank's border halo did not fit the capacity passed to amb_dsm_process_sharded_device
   CTR_DSM_AMBIGUOUS = 4,   // f32 gather: cells re-evaluated exactly because a pair fell inside the guard band
   CTR_ORTHO_CHECK = 8,     // sticky: CHECK(alpha > 0.0), ortho-backward-grid.cc:178
   CTR_PCL_CELLS = 10,      // adaptive OrthoFromPcl: cells listed for the 10^k radius growth
@@ -119,6 +120,16 @@ struct CompactMirror {
   unsigned int* host_flag = nullptr;  // pinned + mapped: set by the pack kernel when a value has no code
   std::vector<cudaEvent_t> chunk_events;
   std::vector<std::thread> workers;   // expander threads of the round in flight
+};
+
+// The neighbours' border halos as delivered by the all-gather (amb_comm.cu): nranks segments of seg_bytes, each a 32-byte
+// header {uint32 count, ...} followed by `capacity` 32-byte records {x, y, z, id}.  The binning kernels read them
+// after the rank's own points; the segment of the rank itself is skipped (those points are already local).
+struct HaloSource {
+  const unsigned char* gathered = nullptr;
+  int nranks = 0, my_rank = 0;
+  unsigned int capacity = 0;
+  size_t seg_bytes = 0;
 };
 
 }  // namespace amb
@@ -146,6 +157,7 @@ struct amb_ctx {
 
   // DSM scratch
   amb::DeviceBuffer points;       // device copy of the caller's xyz (host entry point)
+  amb::DeviceBuffer point_ids;    // device copy of the caller's global point ids (sharded host entry point)
   amb::DeviceBuffer intensities;  // device copy of the caller's intensities (OrthoFromPcl host entry point)
   amb::DeviceBuffer records;      // bucket-sorted 32-byte point records
   amb::DeviceBuffer point_order;  // uint32 per record: canonical (original-index) visiting order inside a bucket
@@ -158,6 +170,10 @@ struct amb_ctx {
   double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
   int dsm_stream_chunks = 1;  // opt-in (> 1): gather + fill in column chunks, each chunk's result mirrored to the host at once
+  // multi-GPU (amb_comm.cu): NCCL communicator this context is a member of, and the halo buffers of the exchange step
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  amb::DeviceBuffer halo_send, halo_recv;
   int dsm_precision = AMB_DSM_F32;  // amb_dsm_set_precision: arithmetic of the tile gather's weights and sums
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;
@@ -207,7 +223,7 @@ void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
             int32_t interpolation_radius, double center_easting, double center_northing, int mode = 0,
-            const int* d_intensities = nullptr);
+            const int* d_intensities = nullptr, const HaloSource* halo = nullptr);
 int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n, double y_lo,
                      double y_hi, double reach, double center_easting, double* d_out_xyz,
                      unsigned long long* d_out_ids, unsigned int capacity, unsigned int* d_count);

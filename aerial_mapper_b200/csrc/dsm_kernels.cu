@@ -89,10 +89,39 @@ __device__ __forceinline__ void load_rec(const PointRec* src, double* x, double*
 
 // ---------------------------------------------------------------------------------------------------------------
 // K1: bucket histogram.  count(b) goes to G[b + 2] so that after the inclusive scan G[b + 1] = start(b).
+// Slot `s` of the gathered halos -> its record, or nullptr (own segment, beyond the segment's count).
+__device__ __forceinline__ const double* halo_record(const HaloSource& h, size_t s) {
+  const unsigned int r = static_cast<unsigned int>(s / h.capacity);
+  const unsigned int k = static_cast<unsigned int>(s - static_cast<size_t>(r) * h.capacity);
+  if (static_cast<int>(r) == h.my_rank) return nullptr;
+  const unsigned char* seg = h.gathered + static_cast<size_t>(r) * h.seg_bytes;
+  if (k >= *reinterpret_cast<const unsigned int*>(seg)) return nullptr;
+  return reinterpret_cast<const double*>(seg + 32) + 4 * static_cast<size_t>(k);
+}
+
 __global__ void __launch_bounds__(256) dsm_count_kernel(const double* __restrict__ xyz, size_t n, DsmPlan plan,
                                                         unsigned int* __restrict__ G,
-                                                        unsigned int* __restrict__ counters) {
+                                                        unsigned int* __restrict__ counters, HaloSource halo) {
   unsigned int local = 0;
+  if (halo.nranks) {  // the neighbours' border points (sharded cloud)
+    const size_t slots = static_cast<size_t>(halo.nranks) * halo.capacity;
+    for (size_t s = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; s < slots;
+         s += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const double* r = halo_record(halo, s);
+      if (!r) continue;
+      int bi, bj;
+      if (fine_bin(plan, r[0] - plan.shift_x, r[1] - plan.shift_y, &bi, &bj)) {
+        const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
+                               static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
+        atomicAdd(&G[b + 2], 1u);
+        ++local;
+      }
+    }
+    if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < halo.nranks) {  // a truncated halo anywhere is an error everywhere
+      const unsigned int c = *reinterpret_cast<const unsigned int*>(halo.gathered + threadIdx.x * halo.seg_bytes);
+      if (c > halo.capacity) atomicExch(&counters[CTR_HALO_OVERFLOW], 1u);
+    }
+  }
   for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < n;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const double px = xyz[3 * t + 0] - plan.shift_x;
@@ -205,7 +234,24 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
                                                           const int* __restrict__ intensities,
                                                           const unsigned long long* __restrict__ ids, size_t n,
                                                           DsmPlan plan, unsigned int* __restrict__ G,
-                                                          PointRec* __restrict__ rec) {
+                                                          PointRec* __restrict__ rec, HaloSource halo) {
+  if (halo.nranks) {
+    const size_t slots = static_cast<size_t>(halo.nranks) * halo.capacity;
+    for (size_t s = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; s < slots;
+         s += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const double* r = halo_record(halo, s);
+      if (!r) continue;
+      const double px = r[0] - plan.shift_x, py = r[1] - plan.shift_y;
+      int bi, bj;
+      if (fine_bin(plan, px, py, &bi, &bj)) {
+        const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
+                               static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
+        const unsigned int code = (static_cast<unsigned int>(bi) << 4) | (static_cast<unsigned int>(bj) & 15u);
+        const unsigned long long id = static_cast<unsigned long long>(__double_as_longlong(r[3])) & 0xffffffffull;
+        store_rec(rec + atomicAdd(&G[b + 1], 1u), px, py, r[2], id | (static_cast<unsigned long long>(code) << 32));
+      }
+    }
+  }
   // Latency-bound chain per point (load -> atomic with return -> store): keep kBatch points in flight per thread.
   constexpr int kBatch = 4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -548,9 +594,11 @@ int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long
 
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
             int32_t interpolation_radius, double center_easting, double center_northing, int mode,
-            const int* d_intensities) {
+            const int* d_intensities, const HaloSource* halo) {
   const amb_geometry& g = ctx->geom;
-  if (n == 0) return AMB_ERR_EMPTY;
+  if (n == 0 && !halo) return AMB_ERR_EMPTY;
+  const size_t n_own = n;
+  if (halo) n += static_cast<size_t>(halo->nranks) * halo->capacity;  // upper bound of the records this rank bins
   if (interpolation_radius < 1 || n >= size_t(0xffffffffu)) return AMB_ERR_INVALID_ARGUMENT;
   const int out_layer = mode == 1 ? AMB_LAYER_ORTHO : AMB_LAYER_ELEVATION;  // ortho-from-pcl.cc:51 / dsm.cc:116
   int st = ensure_layer(ctx, out_layer);
@@ -648,13 +696,14 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   ctx->dsm_launches = 0;
 
   const int stream_grid = kNumSMsB200 * 8;
-  dsm_count_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n, plan, G, counters);
+  const HaloSource hs = halo ? *halo : HaloSource();
+  dsm_count_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n_own, plan, G, counters, hs);
   scan_reduce_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(G), n_vec,
                                                  ctx->block_sums.as<unsigned int>());
   scan_spine_kernel<<<1, 1024, 0, s>>>(ctx->block_sums.as<unsigned int>(), scan_blocks);
   scan_apply_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(G), n_vec,
                                                 ctx->block_sums.as<unsigned int>());
-  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_intensities, d_ids, n, plan, G, rec);
+  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_intensities, d_ids, n_own, plan, G, rec, hs);
   dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
                                                       ctx->point_order.as<unsigned int>());
   ctx->dsm_launches += 6;

@@ -75,6 +75,25 @@ def owner_mask(y_shifted, y_lo, y_hi, rank, world):
     return m
 
 
+def init_comm(ctx, dist, rank, world, device=None):
+    """Make `ctx` (one context per rank) a member of an NCCL communicator owned by the LIBRARY (amb_comm_init): rank 0
+    draws the unique id, torch.distributed only carries its 128 bytes to the other ranks.  Afterwards
+    amb_dsm_process_sharded_device runs the halo exchange on the context's own stream."""
+    import ctypes as C
+    import torch
+    from ._lib import check, lib
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(lib().amb_comm_unique_id(C.cast(buf, C.c_void_p)))
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    idb = (C.c_ubyte * 128).from_buffer_copy(raw)
+    check(lib().amb_comm_init(ctx, int(rank), int(world), C.cast(idb, C.c_void_p)), ctx)
+
+
 class HaloExchange(object):
     """Per-rank state of the border-halo exchange (torch tensors on the rank's device).
 

@@ -204,6 +204,34 @@ int amb_dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_id
                          double reach, double center_easting, double* d_out_xyz, uint64_t* d_out_ids,
                          uint32_t capacity, uint32_t* d_count);
 
+/* ---- the exchange step inside the library (multi-GPU) ----
+ * One context per GPU (one process per GPU, or several contexts in one process) joins an NCCL communicator; NCCL is
+ * loaded at run time (dlopen of libnccl.so.2 — a process that already carries one, e.g. PyTorch's, shares it).
+ *   rank 0:      amb_comm_unique_id(id)            128 bytes; distribute them to every rank by any means
+ *   every rank:  amb_comm_init(ctx, rank, nranks, id)   (collective: blocks until all ranks have called it)
+ * amb_destroy leaves the communicator. */
+int amb_comm_unique_id(void* id128);
+int amb_comm_init(amb_ctx* ctx, int rank, int nranks, const void* id128);
+int amb_comm_destroy(amb_ctx* ctx);
+int amb_comm_size(const amb_ctx* ctx);
+int amb_comm_rank(const amb_ctx* ctx);
+/* Dsm::process on a cloud that arrives sharded by stripe, the exchange included: this rank's points (device memory, global
+ * ids as in amb_dsm_process_device_ids; the rank owns the points whose y - center_easting lies in amb_stripe_y_interval of
+ * its stripe, the outer ranks also what lies beyond the map) -> compaction of the points within amb_dsm_halo_reach of
+ * the stripe borders -> ONE ncclAllGather of the halos (at most halo_capacity points per rank; a larger halo raises
+ * AMB_ERR_SIZE_MISMATCH at the next amb_sync) -> binning over [own points | neighbours' halos] -> the stripe's elevation.
+ * Everything is enqueued on the context's stream: no host synchronisation inside the step.  Collective: every rank of
+ * the communicator must call it.  Without a communicator (or with one rank) it is amb_dsm_process_device_ids.
+ * Bit-identical to the undivided map when every rank passes the same amb_dsm_set_density_hint. */
+int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_ids, size_t n_local,
+                                   int32_t interpolation_radius, double center_easting, double center_northing,
+                                   uint32_t halo_capacity);
+/* Same with this rank's points and ids in HOST memory (copied to the device inside; returns when the stripe's elevation
+ * is final on the device — result layers travel through amb_set_host_mirror / amb_download_layer as usual). */
+int amb_dsm_process_sharded(amb_ctx* ctx, const double* xyz, const uint64_t* ids, size_t n_local,
+                            int32_t interpolation_radius, double center_easting, double center_northing,
+                            uint32_t halo_capacity);
+
 /* Ask the next amb_dsm_process* calls to also record, per cell of the slab, the number of neighbours that
  * entered the IDW sum (result_set.size(), dsm.cc:146) and the index k of the threshold lambda_k*radius that
  * produced them (0 = first query succeeded, 1.. = expanding-radius retries dsm.cc:133-144, -1 = cell untouched). */
