@@ -69,6 +69,7 @@ SYMBOLS = {
     "amb_init_layers": (C.c_int, [_P]),
     "amb_upload_layer": (C.c_int, [_P, C.c_int, _P]),
     "amb_download_layer": (C.c_int, [_P, C.c_int, _P]),
+    "amb_upload_layer_device": (C.c_int, [_P, C.c_int, _P]),
     "amb_download_layer_async": (C.c_int, [_P, C.c_int, _P]),
     "amb_set_host_mirror": (C.c_int, [_P, C.c_int, _P]),
     "amb_set_host_mirror_compact": (C.c_int, [_P, C.c_int, C.c_int]),

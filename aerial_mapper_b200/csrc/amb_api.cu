@@ -296,6 +296,17 @@ int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab) {
   return AMB_OK;
 }
 
+int amb_upload_layer_device(amb_ctx* ctx, int layer, const float* device_slab) {
+  if (!ctx || !device_slab) return AMB_ERR_INVALID_ARGUMENT;
+  AMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int st = ensure_layer(ctx, layer);
+  if (st != AMB_OK) return st;
+  wait_layer_copy(ctx, layer);
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->layers[layer], device_slab, ctx->slab_cells() * sizeof(float),
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+  return AMB_OK;
+}
+
 int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab) {
   if (!ctx || !host_slab) return AMB_ERR_INVALID_ARGUMENT;
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py — grid cells/s of the DSM + orthomosaic hot path (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--dsm-precision f32|f64]
 
-A step is one pass of the hot path over one batch of synthetic input: reset the layers to AerialGridMap's initial
-values, dsm::Dsm::process over the point cloud, ortho::OrthoBackwardGrid::process over the frames (so every step
-does the whole job; nothing is cached between steps).
+Workloads (BASELINE.json configs; synthetic inputs of those shapes, generated in HBM):
+  joint_10k        configs[3] on the GPUs given (default; the >=1e8 cells/s target is quoted on it): 50 M points + 250 gray
+                   4000x3000 frames -> 10000x10000 @ 0.25 m, dsm::Dsm::process then ortho::OrthoBackwardGrid::process
+  dsm_c2           configs[1]: the DSM alone (50 M points -> 10000x10000 @ 0.25 m, radius 1)
+  dsm_c2_holes     the same cloud with 3000 rectangular holes (1-8 m): every retry level of dsm.cc:133-144 and
+                   permanently empty cells (the warp-per-cell kernel)
+  ortho_c3_gray / ortho_c3_color   configs[2]: 250 frames (gray / BGR) -> 8000x8000 @ 0.5 m over an analytic elevation layer
+  incremental_c5   configs[4]: 500 frames in 10 batches of 50 into a 12000x12000 @ 0.25 m grid, layers resident between the
+                   calls (main-ortho-backward-grid-incremental.cc:143-163); a step = the whole stream
+A step resets the layers to AerialGridMap's initial values and does the whole job; nothing is cached between steps.
 
-  value  whole-job cells/s with the inputs already resident in HBM (kernel path, CUDA events / barrier + sync)
-  e2e    the same metric through the public host API (aerial_mapper_b200.Dsm / OrthoBackwardGrid .process with HOST
-         buffers): pinned host -> device copies of points, frames and the layers the path reads, device -> host
-         copies of the layers it writes, all inside the timed region
-  roofline / cpu_baseline   see DESIGN.md §Measurement
+  value  whole-job cells/s with the inputs already resident in HBM: K steps enqueued back to back on the library's
+         stream(s), bracketed by barrier + synchronize, max over ranks
+  e2e    the same metric through the C ABI with HOST buffers (pinned): points / frames host -> device and the result layers
+         device -> host inside the timed region, synchronous calls
+  roofline (one entry per dominant kernel) / cpu_baseline   see DESIGN.md §6
 
 --impl reference times the reference's own CPU implementation (oracle/_ref: dsm.cc, ortho-backward-grid.cc,
 nanoflann.hpp and utils::parFor compiled verbatim against stand-in third-party headers; all host threads) on a
 bounded sample of the same workload; without oracle/_ref it falls back to the restated port and says so (`kind`).
 
-Multi-GPU (torchrun, one rank per GPU): the map is sharded by contiguous column stripes.  The cloud
-arrives sharded the same way (every rank holds the points of its own stripe, with global point ids); frames are
-resident on every rank ("images broadcast once", outside the timed region).  Per step each rank compacts its border
-points (amb_dsm_extract_halo), ONE NCCL all-gather exchanges the halos, then DSM and ortho run on the stripe; the
-result layers stay sharded.  Strong scaling: the job is fixed.
+Multi-GPU (torchrun, one rank per GPU): the map is sharded by contiguous column stripes.  The cloud arrives
+sharded the same way (every rank holds the points of its own stripe, with global ids); frames are resident on every rank
+("images broadcast once", outside the timed region).  Per step each rank runs amb_dsm_process_sharded_device — halo
+compaction, ONE ncclAllGather of the border halos inside the library, binning, gather — then the orthomosaic of its
+stripe; the result layers stay sharded.  Strong scaling: the job is fixed.  Before timing, every rank also evaluates
+the UNDIVIDED map once and compares its stripe bit for bit (`sharded_equals_undivided`); `checksum` is the sum of the
+result layers' bit patterns over all ranks (equal for every N).
 """
 import argparse
 import json
@@ -37,31 +46,48 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+C10K = dict(rows=10000, cols=10000, res=0.25, n_points=50_000_000, lines=10, per_line=25, agl=400.0, cam_scale=1.0,
+            cpu_stripe_cols=400)
 WORKLOADS = {
-    # BASELINE.json configs[3] at one GPU = the configuration north_star quotes the >=1e8 cells/s target on:
-    # 50 M points + 250 frames of 4000x3000 -> 10000x10000 @ 0.25 m (joint DSM + ortho).
-    "joint_10k": dict(rows=10000, cols=10000, res=0.25, n_points=50_000_000, lines=10, per_line=25, agl=400.0,
-                      cam_scale=1.0, cpu_stripe_cols=400),
+    "joint_10k": dict(C10K, dsm=True, ortho=True),
+    "dsm_c2": dict(C10K, dsm=True, ortho=False),
+    "dsm_c2_holes": dict(C10K, dsm=True, ortho=False, holes=3000, hole_sides=(1.0, 8.0)),
+    "ortho_c3_gray": dict(rows=8000, cols=8000, res=0.5, n_points=0, lines=10, per_line=25, agl=600.0, cam_scale=1.0,
+                          cpu_stripe_cols=320, dsm=False, ortho=True),
+    "ortho_c3_color": dict(rows=8000, cols=8000, res=0.5, n_points=0, lines=10, per_line=25, agl=600.0, cam_scale=1.0,
+                           cpu_stripe_cols=320, dsm=False, ortho=True, colored=True),
+    "incremental_c5": dict(rows=12000, cols=12000, res=0.25, n_points=0, lines=20, per_line=25, agl=450.0, cam_scale=1.0,
+                           cpu_stripe_cols=240, dsm=False, ortho=True, batch=50),
     # small variants for tests of this script
-    "joint_1k": dict(rows=1000, cols=1000, res=0.25, n_points=500_000, lines=4, per_line=5, agl=100.0,
-                     cam_scale=0.25, cpu_stripe_cols=40),
-    "joint_256": dict(rows=256, cols=256, res=0.5, n_points=60_000, lines=2, per_line=3, agl=60.0,
-                      cam_scale=0.1, cpu_stripe_cols=32),
+    "joint_1k": dict(rows=1000, cols=1000, res=0.25, n_points=500_000, lines=4, per_line=5, agl=100.0, cam_scale=0.25,
+                     cpu_stripe_cols=40, dsm=True, ortho=True),
+    "joint_256": dict(rows=256, cols=256, res=0.5, n_points=60_000, lines=2, per_line=3, agl=60.0, cam_scale=0.1,
+                      cpu_stripe_cols=32, dsm=True, ortho=True),
+    "dsm_256_holes": dict(rows=256, cols=256, res=0.5, n_points=60_000, lines=2, per_line=3, agl=60.0, cam_scale=0.1,
+                          cpu_stripe_cols=32, dsm=True, ortho=False, holes=12, hole_sides=(2.0, 9.0)),
+    "ortho_256_color": dict(rows=256, cols=256, res=0.5, n_points=0, lines=2, per_line=3, agl=60.0, cam_scale=0.1,
+                            cpu_stripe_cols=32, dsm=False, ortho=True, colored=True),
+    "incremental_256": dict(rows=256, cols=256, res=0.5, n_points=0, lines=2, per_line=4, agl=60.0, cam_scale=0.1,
+                            cpu_stripe_cols=32, dsm=False, ortho=True, batch=2),
 }
 
-DSM_BYTES_PER_POINT = 24  # read each point once
-DSM_BYTES_PER_CELL = 4    # write each elevation once
+DSM_BYTES_PER_POINT = 24   # read each point once
+DSM_BYTES_PER_CELL = 4     # write each elevation once
+ORTHO_BYTES_PER_CELL = 20  # read elevation + elevation_angle, write elevation_angle + observation_index + ortho (+ texel bytes)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="joint_10k", choices=sorted(WORKLOADS))
+    ap.add_argument("--dsm-precision", default=None, choices=["f32", "f64"],
+                    help="arithmetic of the DSM gather's weights/sums (default: the library's, f32; neighbour sets exact in both)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the sharded == undivided comparison")
     return ap.parse_args()
 
 
@@ -79,7 +105,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -128,8 +154,27 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def workload_inputs(wl):
+    """Geometry, camera and poses of a workload (host side, cheap)."""
+    from aerial_mapper_b200 import synth
+    rows, cols, res = wl["rows"], wl["cols"], wl["res"]
+    half_x, half_y = rows * res / 2, cols * res / 2
+    camd = synth.scaled_camera(wl["cam_scale"]) if wl["cam_scale"] != 1.0 else dict(synth.C3_CAMERA)
+    poses = synth.lawnmower_poses(wl["lines"], wl["per_line"], half_x, half_y, wl["agl"], seed=4)
+    return rows, cols, res, half_x, half_y, camd, poses
+
+
+def hole_rectangles(wl, half_x, half_y):
+    """(cx, cy, sx, sy) of the holes of a `*_holes` workload (seeded; the same for the GPU and the CPU arm)."""
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = wl.get("holes", 0)
+    lo, hi = wl.get("hole_sides", (1.0, 8.0))
+    return np.c_[rng.uniform(-half_x, half_x, n), rng.uniform(-half_y, half_y, n), rng.uniform(lo, hi, n),
+                 rng.uniform(lo, hi, n)]
+
+
 # --------------------------------------------------------------------------------------------------------------
-def device_point_cloud(torch, n, half_x, half_y, device, seed=2):
+def device_point_cloud(torch, n, half_x, half_y, device, seed=2, holes=None):
     """config C2 points generated in HBM (same distribution as synth.point_cloud; torch RNG, seeded)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -138,13 +183,62 @@ def device_point_cloud(torch, n, half_x, half_y, device, seed=2):
     xyz[:, 1] = (torch.rand(n, generator=g, device=device, dtype=torch.float64) * 2 - 1) * half_y
     xyz[:, 2] = (100.0 + 10.0 * torch.sin(0.01 * xyz[:, 0]) * torch.cos(0.01 * xyz[:, 1]) +
                  0.05 * torch.randn(n, generator=g, device=device, dtype=torch.float64))
+    if holes is not None and len(holes):
+        # delete the points inside the rectangles: coarse 1 m occupancy raster of the holes, then the exact test per hole
+        # only for the points whose raster cell is touched (3000 exact tests over 50 M points would take minutes)
+        nx, ny = int(2 * half_x) + 2, int(2 * half_y) + 2
+        occ = torch.zeros((nx, ny), dtype=torch.bool, device=device)
+        for cx, cy, sx, sy in holes:
+            i0, i1 = int(cx - sx / 2 + half_x) - 1, int(cx + sx / 2 + half_x) + 2
+            j0, j1 = int(cy - sy / 2 + half_y) - 1, int(cy + sy / 2 + half_y) + 2
+            occ[max(i0, 0):max(i1, 0), max(j0, 0):max(j1, 0)] = True
+        ci = (xyz[:, 0] + half_x).long().clamp_(0, nx - 1)
+        cj = (xyz[:, 1] + half_y).long().clamp_(0, ny - 1)
+        cand = occ[ci, cj].nonzero().squeeze(1)
+        px, py = xyz[cand, 0], xyz[cand, 1]
+        inside = torch.zeros(cand.shape[0], dtype=torch.bool, device=device)
+        h = torch.as_tensor(np.asarray(holes), device=device)
+        for k0 in range(0, h.shape[0], 64):
+            hk = h[k0:k0 + 64]
+            inside |= ((px[:, None] - hk[None, :, 0]).abs() < 0.5 * hk[None, :, 2]).logical_and(
+                (py[:, None] - hk[None, :, 1]).abs() < 0.5 * hk[None, :, 3]).any(dim=1)
+        keep = torch.ones(n, dtype=torch.bool, device=device)
+        keep[cand[inside]] = False
+        xyz = xyz[keep].contiguous()
     return xyz
+
+
+def layer_bits_sum(torch, gm, names, c0, c1):
+    """Sum of the uint32 bit patterns of the stripe's result layers (device side), as a python int."""
+    import ctypes as C
+    import aerial_mapper_b200 as amb
+    from aerial_mapper_b200 import _lib
+    rows = gm.geometry.rows
+    total = 0
+    for name in names:
+        p = C.c_void_p()
+        amb.check(amb.lib().amb_layer_device_ptr(gm.context(), _lib.LAYER_ID[name], C.byref(p)), gm.context())
+        t = tensor_from_ptr(torch, p.value, rows * (c1 - c0), torch.int32, gm._device)
+        total += int((t.to(torch.int64) & 0xffffffff).sum().item())
+    return total
+
+
+def tensor_from_ptr(torch, ptr, count, dtype, device_index):
+    """A torch view of library-owned device memory (plumbing for checksums / comparisons only)."""
+    itemsize = torch.empty((), dtype=dtype).element_size()
+
+    class _Holder(object):
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (count,), "typestr": {4: "<i4", 8: "<i8", 1: "|u1"}[itemsize],
+                                  "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device=torch.device("cuda", device_index))
 
 
 def run_ours(args):
     import torch
     import aerial_mapper_b200 as amb
-    from aerial_mapper_b200 import synth
+    from aerial_mapper_b200 import synth, sharding, _lib
     import ctypes as C
 
     rank = int(os.environ.get("RANK", "0"))
@@ -156,6 +250,8 @@ def run_ours(args):
                              (args.gpus, args.gpus))
     if amb.lib().amb_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    if args.dsm_precision:
+        os.environ["AMB_DSM_PRECISION"] = args.dsm_precision  # read by the library at amb_create
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist = None
@@ -166,64 +262,95 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
 
     wl = WORKLOADS[args.workload]
-    rows, cols, res = wl["rows"], wl["cols"], wl["res"]
-    half_x, half_y = rows * res / 2, cols * res / 2
+    rows, cols, res, half_x, half_y, camd, poses = workload_inputs(wl)
     cells = rows * cols
-    camd = synth.scaled_camera(wl["cam_scale"]) if wl["cam_scale"] != 1.0 else dict(synth.C3_CAMERA)
-    poses = synth.lawnmower_poses(wl["lines"], wl["per_line"], half_x, half_y, wl["agl"], seed=4)
-    n_frames = len(poses)
+    do_dsm, do_ortho = wl["dsm"], wl["ortho"]
+    colored = bool(wl.get("colored", False))
+    channels = 3 if colored else 1
+    batch = wl.get("batch", 0)
+    n_frames = len(poses) if do_ortho else 0
     W, H = camd["width"], camd["height"]
-
-    # column stripe of this rank
-    from aerial_mapper_b200 import sharding
+    out_name = "colored_ortho" if colored else "ortho"
     c0, c1 = sharding.stripe_range(cols, rank, world)
     if c1 <= c0:
         raise SystemExit("bench.py: more ranks than map columns")
 
     # ---- synthetic inputs, generated in HBM ----
-    xyz_d = device_point_cloud(torch, wl["n_points"], half_x, half_y, device)
-    imgs_d = synth.procedural_images_torch(n_frames, W, H, 1, device)
+    xyz_d = None
+    if do_dsm:
+        xyz_d = device_point_cloud(torch, wl["n_points"], half_x, half_y, device,
+                                   holes=hole_rectangles(wl, half_x, half_y) if wl.get("holes") else None)
+    imgs_d, img_ptrs = None, []
+    if do_ortho:
+        imgs_d = synth.procedural_images_torch(n_frames, W, H, channels, device)
+        img_ptrs = [imgs_d[k].data_ptr() for k in range(n_frames)]
+    elev_host = None
+    if do_ortho and not do_dsm:
+        elev_host = synth.analytic_elevation(rows, cols, res)
     torch.cuda.synchronize()
-    n_points = xyz_d.shape[0]
-    img_ptrs = [imgs_d[k].data_ptr() for k in range(n_frames)]
+    n_points = int(xyz_d.shape[0]) if do_dsm else 0
 
-    layer_names = ("ortho", "elevation", "elevation_angle", "observation_index")
+    layer_names = tuple(n for n in (out_name, "elevation", "elevation_angle", "observation_index")
+                        if do_ortho or n == "elevation")
+    result_names = ("elevation",) if not do_ortho else ((out_name, "elevation_angle", "observation_index") +
+                                                        (("elevation",) if do_dsm else ()))
     settings = amb.GridMapSettings(0.0, 0.0, rows * res, cols * res, res)
-    agm = amb.AerialGridMap(settings, pinned=True, layer_names=layer_names)
-    gm = agm.getMutable()
-    gm.to_device(local_rank, col_range=(c0, c1), names=layer_names)
+
+    def make_map(col_range, pinned):
+        agm = amb.AerialGridMap(settings, pinned=pinned, layer_names=layer_names)
+        gm_ = agm.getMutable()
+        if elev_host is not None:
+            gm_.layers["elevation"][...] = elev_host
+        gm_.to_device(local_rank, col_range=col_range, names=layer_names)
+        return agm, gm_
+
+    agm, gm = make_map((c0, c1), pinned=False)
     ctx = gm.context()
     dsm = amb.Dsm(amb.DsmSettings(), gm)
-    ortho = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=False), gm)
+    ortho = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=colored), gm) if do_ortho else None
+    elev_dev_stripe = None
+    if elev_host is not None:   # ortho-only workloads: the elevation layer is an input, re-uploaded by nobody: keep a copy
+        p = C.c_void_p()
+        amb.check(amb.lib().amb_layer_device_ptr(ctx, _lib.LAYER_ID["elevation"], C.byref(p)), ctx)
+        elev_dev_stripe = tensor_from_ptr(torch, p.value, rows * (c1 - c0), torch.int32, local_rank).clone()
 
-    hx = None
+    # ---- N>1: shard the cloud by stripe (setup, outside the timed region) and join the library's communicator ----
+    local_xyz = local_ids = None
+    halo_cap = 0
+    n_local = n_points
     if world > 1:
-        # shard the cloud by stripe (setup, outside the timed region): global ids keep the summation order of the
-        # undivided map, so the sharded result is bit-identical to the single-GPU one
-        y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
-        reach = amb.lib().amb_dsm_halo_reach(C.byref(gm.geometry), 1)
-        own = sharding.owner_mask(xyz_d[:, 1], y_lo, y_hi, rank, world)
-        ids_all = torch.arange(n_points, dtype=torch.int64, device=device)
-        cap = int(n_points * (2.0 * reach) / (2.0 * half_y) * 1.5) + 4096
-        hx = sharding.HaloExchange(torch, world, rank, cap, xyz_d[own], ids_all[own], device)
-        amb.check(amb.lib().amb_dsm_set_density_hint(ctx, n_points / float(rows * cols)), ctx)
-        if os.environ.get("AMB_BENCH_STREAM_HALO") == "1":
-            # opt-in: torch plumbing + NCCL on the library's own stream, no host sync inside the halo step
-            hx.use_stream(torch.cuda.ExternalStream(amb.lib().amb_stream(ctx), device=device))
-        del xyz_d, ids_all, own
-        torch.cuda.empty_cache()
+        sharding.init_comm(ctx, dist, rank, world, device)
+        if do_dsm:
+            y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
+            reach = amb.lib().amb_dsm_halo_reach(C.byref(gm.geometry), 1)
+            own = sharding.owner_mask(xyz_d[:, 1], y_lo, y_hi, rank, world)
+            local_xyz = xyz_d[own].contiguous()
+            local_ids = torch.arange(n_points, dtype=torch.int64, device=device)[own].contiguous()
+            n_local = int(local_xyz.shape[0])
+            halo_cap = int(n_points * (2.0 * reach) / (2.0 * half_y) * 1.3) + 4096
+            amb.check(amb.lib().amb_dsm_set_density_hint(ctx, n_points / float(rows * cols)), ctx)
+            del own
 
-    def step_resident():
-        amb.check(amb.lib().amb_init_layers(ctx), ctx)
-        if world > 1:
-            hx.extract(ctx, y_lo, y_hi, reach)   # compaction kernel on the library's stream
-            hx.exchange(dist)                    # the one collective of the step (border halos)
-            hx.assemble()
-            dsm.process_device(hx.big_xyz.data_ptr(), hx.n_total, gm, d_ids=hx.big_ids.data_ptr())
-        else:
-            dsm.process_device(xyz_d.data_ptr(), n_points, gm)
-        ortho.process_device(poses, img_ptrs, W, gm)
-        gm.sync()
+    def reset_layers(ctx_, gm_):
+        amb.check(amb.lib().amb_init_layers(ctx_), ctx_)
+        if elev_host is not None:   # ortho-only: put the input elevation back (device -> device, the stripe only)
+            src_ = elev_dev_stripe if gm_ is gm else elev_full_dev
+            amb.check(amb.lib().amb_upload_layer_device(ctx_, _lib.LAYER_ID["elevation"], C.c_void_p(src_.data_ptr())), ctx_)
+
+    def enqueue_step(gm_, dsm_, ortho_, sharded):
+        ctx_ = gm_.context()
+        reset_layers(ctx_, gm_)
+        if do_dsm:
+            if sharded:
+                dsm_.process_sharded_device(local_xyz.data_ptr(), local_ids.data_ptr(), n_local, gm_, halo_cap)
+            else:
+                dsm_.process_device(xyz_d.data_ptr(), n_points, gm_)
+        if do_ortho:
+            if batch:
+                for b0 in range(0, n_frames, batch):
+                    ortho_.process_device(poses[b0:b0 + batch], img_ptrs[b0:b0 + batch], W * channels, gm_)
+            else:
+                ortho_.process_device(poses, img_ptrs, W * channels, gm_)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,99 +358,118 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM ----
+    # ---- N>1: the sharded result must equal the undivided map bit for bit (every rank checks its own stripe) ----
+    verify = None
+    elev_full_dev = None
+    if world > 1 and not args.no_verify:
+        agm_f, gm_f = make_map((0, cols), pinned=False)
+        if elev_host is not None:
+            p = C.c_void_p()
+            amb.check(amb.lib().amb_layer_device_ptr(gm_f.context(), _lib.LAYER_ID["elevation"], C.byref(p)), gm_f.context())
+            elev_full_dev = tensor_from_ptr(torch, p.value, rows * cols, torch.int32, local_rank).clone()
+        dsm_f = amb.Dsm(amb.DsmSettings(), gm_f)
+        ortho_f = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=colored), gm_f) if do_ortho else None
+        enqueue_step(gm_f, dsm_f, ortho_f, sharded=False)
+        gm_f.sync()
+        enqueue_step(gm, dsm, ortho, sharded=True)
+        gm.sync()
+        same = True
+        for name in result_names:
+            pf, ps = C.c_void_p(), C.c_void_p()
+            amb.check(amb.lib().amb_layer_device_ptr(gm_f.context(), _lib.LAYER_ID[name], C.byref(pf)), gm_f.context())
+            amb.check(amb.lib().amb_layer_device_ptr(ctx, _lib.LAYER_ID[name], C.byref(ps)), ctx)
+            tf = tensor_from_ptr(torch, pf.value, rows * cols, torch.int32, local_rank)[rows * c0:rows * c1]
+            ts = tensor_from_ptr(torch, ps.value, rows * (c1 - c0), torch.int32, local_rank)
+            same = same and bool(torch.equal(tf, ts))
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verify = bool(flag.item())
+        del gm_f, agm_f, dsm_f, ortho_f
+        elev_full_dev = None
+        torch.cuda.empty_cache()
+    if world > 1 and do_dsm:
+        del xyz_d   # only this rank's share stays resident
+        xyz_d = None
+        torch.cuda.empty_cache()
+
+    # ---- value: inputs resident in HBM, K steps back to back ----
+    sharded = world > 1 and do_dsm
     for _ in range(args.warmup):
-        step_resident()
+        enqueue_step(gm, dsm, ortho, sharded)
+    gm.sync()
     barrier()
-    if world > 1 and (hx.counts() > hx.cap).any():
-        raise SystemExit("bench.py: border halo truncated (capacity %d, counts %s)" % (hx.cap, hx.counts()))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gather_ms, bin_ms, fill_ms, ortho_ms, launches = [], [], [], [], 0
     t0 = time.perf_counter()
-    ev0.record()
     for _ in range(args.steps):
-        step_resident()
-        tm = gm.timings()  # CUDA events on the library's stream; the stream is already idle here
-        gather_ms.append(tm["dsm_gather_ms"])
-        bin_ms.append(tm["dsm_bin_ms"])
-        fill_ms.append(tm["dsm_fill_ms"])
-        ortho_ms.append(tm["ortho_kernel_ms"])
-        launches += tm["dsm_kernel_launches"] + tm["ortho_kernel_launches"] + len(layer_names) + (1 if world > 1 else 0)
-    ev1.record()
+        enqueue_step(gm, dsm, ortho, sharded)
+    gm.sync()          # one synchronisation for the K steps (also reports any deferred reference CHECK / halo overflow)
+    torch.cuda.synchronize()
+    my_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ms_total = max(ev0.elapsed_time(ev1), 1e-6)
-    # torch's events sit on torch's stream while the library runs on its own; the host-side sync inside every step
-    # makes both clocks agree — take the larger of the two to be safe.
-    ms_total = max(ms_total, wall_ms)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    t = torch.tensor([my_ms], dtype=torch.float64, device=device)
+    all_ms = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(all_ms, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = cells / (ms_step * 1e-3)
+    rank_ms_per_step = [float(x.item()) / args.steps for x in all_ms] if world > 1 else [ms_step]
 
-    # ---- e2e: host buffers through the public API ----
+    # stage breakdown + checksum: a few more steps, synchronised one by one (not part of the timed region)
+    stage = {"dsm_halo": [], "dsm_bin": [], "dsm_gather": [], "dsm_fill": [], "ortho": []}
+    launches_per_step = 0
+    for _ in range(3):
+        enqueue_step(gm, dsm, ortho, sharded)
+        gm.sync()
+        tm = gm.timings()
+        stage["dsm_halo"].append(tm["dsm_h2d_ms"])
+        stage["dsm_bin"].append(tm["dsm_bin_ms"])
+        stage["dsm_gather"].append(tm["dsm_gather_ms"])
+        stage["dsm_fill"].append(tm["dsm_fill_ms"])
+        stage["ortho"].append(tm["ortho_kernel_ms"] * (n_frames // batch if batch else 1))
+        launches_per_step = (len(layer_names) + (tm["dsm_kernel_launches"] + (2 if sharded else 0) if do_dsm else 0) +
+                             (tm["ortho_kernel_launches"] * (n_frames // batch if batch else 1) if do_ortho else 0))
+        cells_exact = tm["dsm_cells_empty"]
+    stage_ms = {k: float(np.mean(v)) for k, v in stage.items()}
+    csum = torch.tensor([layer_bits_sum(torch, gm, result_names, c0, c1) % (1 << 62)], dtype=torch.int64, device=device)
+    smax = torch.tensor([stage_ms[k] for k in ("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho")],
+                        dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+    checksum = int(csum.item()) % (1 << 62)
+    stage_ms = dict(zip(("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho"), [float(x) for x in smax.tolist()]))
+
+    # incremental workload: the batched stream must end in the same ortho / elevation_angle layers as one call over all
+    # frames (observation_index holds the index WITHIN a process() call, so it legitimately differs)
+    incremental_ok = None
+    if batch and world == 1:
+        keep = {}
+        cmp_names = (out_name, "elevation_angle")
+        for name in cmp_names:
+            p = C.c_void_p()
+            amb.check(amb.lib().amb_layer_device_ptr(ctx, _lib.LAYER_ID[name], C.byref(p)), ctx)
+            keep[name] = tensor_from_ptr(torch, p.value, rows * (c1 - c0), torch.int32, local_rank).clone()
+        reset_layers(ctx, gm)
+        ortho.process_device(poses, img_ptrs, W * channels, gm)
+        gm.sync()
+        incremental_ok = True
+        for name in cmp_names:
+            p = C.c_void_p()
+            amb.check(amb.lib().amb_layer_device_ptr(ctx, _lib.LAYER_ID[name], C.byref(p)), ctx)
+            incremental_ok = incremental_ok and bool(torch.equal(
+                keep[name], tensor_from_ptr(torch, p.value, rows * (c1 - c0), torch.int32, local_rank)))
+        del keep
+
+    # ---- e2e: host buffers through the C ABI ----
     e2e = None
     if not args.no_e2e:
-        n_host = n_points if world == 1 else hx.n_local
-        xyz_h = torch.empty((n_host, 3), dtype=torch.float64, pin_memory=True)
-        xyz_h.copy_(xyz_d if world == 1 else hx.local_xyz)
-        imgs_h = torch.empty((n_frames, H, W), dtype=torch.uint8, pin_memory=True)
-        imgs_h.copy_(imgs_d)
-        torch.cuda.synchronize()
-        xyz_np = xyz_h.numpy()
-        img_np = [imgs_h[k].numpy() for k in range(n_frames)]
-        gm_h = amb.AerialGridMap(settings, pinned=True, layer_names=layer_names)
-        gmh = gm_h.getMutable()
-        gmh.to_device(local_rank, col_range=(c0, c1), names=layer_names)  # layers live in HBM between calls
-        ctx_h = gmh.context()
-        gmh.set_mirrors(layer_names)   # result layers stream back to the (pinned) host map as they become final
-        if world > 1:
-            amb.check(amb.lib().amb_dsm_set_density_hint(ctx_h, n_points / float(rows * cols)), ctx_h)
-        dsm_h = amb.Dsm(amb.DsmSettings(), gmh)
-        ortho_h = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=False), gmh)
-        slab_bytes = rows * (c1 - c0) * 4
-
-        def step_e2e():
-            amb.check(amb.lib().amb_init_layers(ctx_h), ctx_h)  # AerialGridMap::initialize values, device side
-            if world > 1:
-                hx.use_stream(torch.cuda.ExternalStream(amb.lib().amb_stream(ctx_h), device=device)
-                              if os.environ.get("AMB_BENCH_STREAM_HALO") == "1" else None)
-                with hx._on_stream():
-                    hx.local_xyz.copy_(xyz_h, non_blocking=True)   # this rank's share of the cloud: host -> device
-                hx.extract(ctx_h, y_lo, y_hi, reach)
-                hx.exchange(dist)
-                hx.assemble()
-                dsm_h.process_device(hx.big_xyz.data_ptr(), hx.n_total, gmh, d_ids=hx.big_ids.data_ptr())
-            else:
-                dsm_h.process(xyz_np, gmh)        # amb_dsm_process: HOST points -> H2D inside
-            ortho_h.process(poses, img_np, gmh)   # amb_ortho_process: HOST frames -> needed sub-rectangles H2D
-            gmh.sync()                            # amb_sync: all four result layers are in host memory
-
-        e2e_steps = max(1, min(args.steps, 3))
-        step_e2e()
-        ortho_h2d = gmh.timings()["ortho_h2d_bytes"]
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_e2e()
-        barrier()
-        te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = n_host * 24 + int(ortho_h2d) + n_frames * 7 * 8
-        d2h = 4 * slab_bytes
-        e2e = {"value": cells / float(te.item()), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
-               "frames_host_bytes": int(n_frames * H * W),
-               "api": "C ABI through the Python mirror, HOST inputs/outputs (pinned): amb_init_layers, "
-                      "amb_dsm_process(host xyz), amb_ortho_process(host frames; only the winners' "
-                      "sub-rectangles cross PCIe), result layers through amb_set_host_mirror (x4), amb_sync"}
-        del gm_h, gmh
+        e2e = run_e2e(args, torch, amb, sharding, C, dist, device, local_rank, rank, world, wl, settings, layer_names,
+                      result_names, camd, poses, colored, channels, batch, (c0, c1), xyz_d, local_xyz, local_ids,
+                      imgs_d, elev_host, n_points, halo_cap, barrier)
 
     if rank != 0:
         if dist is not None:
@@ -332,42 +478,59 @@ def run_ours(args):
 
     peak, peak_src = measured_peak_hbm()
     stripe_cells = rows * (c1 - c0)
-    n_rank_points = n_points if world == 1 else hx.n_total
-    alg_bytes = DSM_BYTES_PER_POINT * n_rank_points + DSM_BYTES_PER_CELL * stripe_cells
-    g_ms = float(np.mean(gather_ms))
-    achieved = alg_bytes / (g_ms * 1e-3) / 1e9
-    traffic, compute_note = None, None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    traffic_db = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            if world == 1:
-                cap = json.load(f)[args.workload]["dsm_gather_kernel"]
-                traffic = cap["traffic_bytes_per_launch"]
-                if "fp64_pipe_active_pct" in cap:  # same capture: why the HBM fraction is low
-                    compute_note = {"fp64_pipe_active_pct": cap["fp64_pipe_active_pct"],
-                                    "issue_active_pct": cap.get("issue_active_pct"),
-                                    "source": cap.get("compute_source")}
+            traffic_db = json.load(f).get(args.workload, {}) if world == 1 else {}
     except Exception:
-        traffic, compute_note = None, None
-    roofline = {"bound": "hbm", "kernel": "dsm_gather_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": g_ms,
-                "stage_ms": {"dsm_bin": float(np.mean(bin_ms)), "dsm_gather": g_ms,
-                             "dsm_fill": float(np.mean(fill_ms)), "ortho": float(np.mean(ortho_ms))}}
-    if compute_note is not None:
-        roofline["compute_capture"] = compute_note
+        traffic_db = {}
+    lib_prec = "f64" if os.environ.get("AMB_DSM_PRECISION", "f32").lower().startswith("f6") else "f32"
+    gather_kernel = "dsm_gather_kernel_f32" if lib_prec == "f32" else "dsm_gather_kernel"
+    roof = []
+    if do_dsm:
+        n_rank_points = n_points if world == 1 else n_local
+        alg = DSM_BYTES_PER_POINT * n_rank_points + DSM_BYTES_PER_CELL * stripe_cells
+        ach = alg / (stage_ms["dsm_gather"] * 1e-3) / 1e9
+        cap = traffic_db.get(gather_kernel, {})
+        roof.append({"kernel": gather_kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": cap.get("traffic_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": int(alg), "kernel_ms": stage_ms["dsm_gather"],
+                     "issue_active_pct": cap.get("issue_active_pct"), "fp64_pipe_active_pct": cap.get("fp64_pipe_active_pct"),
+                     "limiter": cap.get("limiter", "instruction issue (see profiles/), not HBM")})
+    if do_ortho:
+        launches = (n_frames // batch) if batch else 1
+        alg = (ORTHO_BYTES_PER_CELL + channels) * stripe_cells
+        ms_launch = stage_ms["ortho"] / launches
+        ach = alg / (ms_launch * 1e-3) / 1e9
+        cap = traffic_db.get("ortho_kernel_dom", {})
+        roof.append({"kernel": "ortho_kernel_dom", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": cap.get("traffic_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": int(alg), "kernel_ms": ms_launch, "launches_per_step": launches,
+                     "issue_active_pct": cap.get("issue_active_pct"), "fp64_pipe_active_pct": cap.get("fp64_pipe_active_pct"),
+                     "limiter": cap.get("limiter", "latency / occupancy + FP64 pipe (see profiles/), not HBM")})
+    dom = max(roof, key=lambda r: r["kernel_ms"] * r.get("launches_per_step", 1))
+    roofline = dict(dom)   # the contract's single object = the dominant kernel; `kernels` lists all
+    roofline.update({"peak_source": peak_src, "stage_ms": stage_ms, "kernels": roof})
     out = {"metric": "grid cells/sec (DSM+ortho)", "value": value, "unit": "cells/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "scaling": "strong", "vs_baseline": None,
+           "dtype": ("f32 (DSM weights/sums; neighbour decisions exact vs f64) + f64 (orthomosaic)" if lib_prec == "f32"
+                     else "f64") if do_dsm else "f64",
+           "data": "synthetic",
            "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res), "points": int(n_points),
-                      "frames": "%dx %dx%d gray" % (n_frames, W, H), "interpolation_radius": 1,
-                      "sharding": ("column stripes x%d; cloud sharded by stripe; 1 all-gather of border halos/step; layers "
-                                   "stay sharded" % world) if world > 1 else "single GPU",
-                      "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W) / 1e9),
-                      "ortho_dominance_cull": bool(getattr(ortho, "dominance_cull", False)),    # opt-in (AMB_ORTHO_DOMINANCE=1)
-                      "dsm_balanced_gather": bool(getattr(dsm, "balanced_gather", False)),
-                      "dsm_stream_chunks": int(getattr(dsm, "stream_chunks", 1)),      # opt-in (AMB_DSM_STREAM_CHUNKS=K)
-                      "compact_mirrors": os.environ.get("AMB_COMPACT_MIRRORS", "0") not in ("", "0")},  # opt-in, e2e only     # opt-in (AMB_DSM_BALANCED_GATHER=1)
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+                      "frames": ("%dx %dx%d %s" % (n_frames, W, H, "BGR" if colored else "gray")) if do_ortho else "none",
+                      "frame_batches": (n_frames // batch) if batch else (1 if do_ortho else 0),
+                      "interpolation_radius": 1, "dsm_precision": lib_prec if do_dsm else None,
+                      "sharding": ("column stripes x%d; cloud sharded by stripe; 1 ncclAllGather of border halos per step "
+                                   "inside the library; layers stay sharded" % world) if world > 1 else "single GPU",
+                      "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W * channels) / 1e9),
+                      "timed_region": "K steps enqueued back to back, one synchronisation at the end"},
+           "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline,
+           "checksum": checksum, "rank_ms_per_step": rank_ms_per_step, "dsm_cells_exact_path": int(cells_exact)}
+    if verify is not None:
+        out["sharded_equals_undivided"] = verify
+    if incremental_ok is not None:
+        out["incremental_equals_single_call"] = incremental_ok
     if e2e is not None:
         out["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
@@ -375,6 +538,97 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_e2e(args, torch, amb, sharding, C, dist, device, local_rank, rank, world, wl, settings, layer_names,
+            result_names, camd, poses, colored, channels, batch, col_range, xyz_d, local_xyz, local_ids, imgs_d,
+            elev_host, n_points, halo_cap, barrier):
+    """The same job through the C ABI with HOST inputs and outputs (pinned): amb_init_layers, amb_dsm_process /
+    amb_dsm_process_sharded (host points), amb_ortho_process (host frames: only the winners' sub-rectangles cross PCIe),
+    result layers through amb_set_host_mirror, amb_sync — host<->device copies inside the timed region."""
+    from aerial_mapper_b200 import _lib
+    do_dsm, do_ortho = wl["dsm"], wl["ortho"]
+    rows, cols = wl["rows"], wl["cols"]
+    c0, c1 = col_range
+    W, H = camd["width"], camd["height"]
+    n_frames = len(poses) if do_ortho else 0
+    sharded = world > 1 and do_dsm
+    xyz_np = ids_np = None
+    n_host = 0
+    if do_dsm:
+        src = local_xyz if sharded else xyz_d
+        n_host = int(src.shape[0])
+        xyz_h = torch.empty((n_host, 3), dtype=torch.float64, pin_memory=True)
+        xyz_h.copy_(src)
+        xyz_np = xyz_h.numpy()
+        if sharded:
+            ids_h = torch.empty(n_host, dtype=torch.int64, pin_memory=True)
+            ids_h.copy_(local_ids)
+            ids_np = ids_h.numpy().view(np.uint64)
+    img_np = []
+    if do_ortho:
+        shape = (n_frames, H, W, 3) if colored else (n_frames, H, W)
+        imgs_h = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+        imgs_h.copy_(imgs_d)
+        img_np = [imgs_h[k].numpy() for k in range(n_frames)]
+    torch.cuda.synchronize()
+    gm_h = amb.AerialGridMap(settings, pinned=True, layer_names=layer_names)
+    gmh = gm_h.getMutable()
+    if elev_host is not None:
+        gmh.layers["elevation"][...] = elev_host
+    gmh.to_device(local_rank, col_range=(c0, c1), names=layer_names)   # layers live in HBM between the calls
+    ctx_h = gmh.context()
+    gmh.set_mirrors(result_names)   # result layers stream back to the (pinned) host map as they become final
+    if world > 1:
+        sharding.init_comm(ctx_h, dist, rank, world, device)
+        amb.check(amb.lib().amb_dsm_set_density_hint(ctx_h, n_points / float(rows * cols)), ctx_h)
+    dsm_h = amb.Dsm(amb.DsmSettings(), gmh)
+    ortho_h = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=colored), gmh) if do_ortho else None
+    slab_bytes = rows * (c1 - c0) * 4
+    elev_slab = np.ascontiguousarray(elev_host[:, c0:c1].T).T if elev_host is not None else None
+
+    def step_e2e():
+        amb.check(amb.lib().amb_init_layers(ctx_h), ctx_h)   # AerialGridMap::initialize values, device side
+        if elev_host is not None:                            # ortho-only: the input layer travels host -> device
+            amb.check(amb.lib().amb_upload_layer(ctx_h, _lib.LAYER_ID["elevation"],
+                                                 gmh._slab("elevation").ctypes.data_as(C.c_void_p)), ctx_h)
+        if do_dsm:
+            if sharded:
+                dsm_h.process_sharded(xyz_np, ids_np, gmh, halo_cap)
+            else:
+                dsm_h.process(xyz_np, gmh)
+        if do_ortho:
+            if batch:
+                for b0 in range(0, n_frames, batch):
+                    ortho_h.process(poses[b0:b0 + batch], img_np[b0:b0 + batch], gmh)
+            else:
+                ortho_h.process(poses, img_np, gmh)
+        gmh.sync()   # every result layer is in host memory
+
+    e2e_steps = max(1, min(args.steps, 10))
+    step_e2e()
+    ortho_h2d = gmh.timings()["ortho_h2d_bytes"] if do_ortho else 0
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    te_local = (time.perf_counter() - t0) / e2e_steps
+    barrier()
+    te = torch.tensor([te_local], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d = n_host * (24 + (8 if sharded else 0)) + int(ortho_h2d) * (len(poses) // batch if batch else 1) + \
+        n_frames * 7 * 8 + (slab_bytes if elev_host is not None else 0)
+    d2h = len(result_names) * slab_bytes
+    del gm_h, gmh
+    return {"value": rows * cols / float(te.item()), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
+            "frames_host_bytes": int(n_frames * H * W * channels),
+            "api": "C ABI through the Python mirror, HOST inputs/outputs (pinned): amb_init_layers, "
+                   "amb_dsm_process%s(host xyz), amb_ortho_process(host frames; only the winners' sub-rectangles "
+                   "cross PCIe), result layers through amb_set_host_mirror (x%d), amb_sync"
+                   % ("_sharded" if sharded else "", len(result_names))}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -385,87 +639,107 @@ def cpu_reference(args, steps, warmup):
     from oracle import pyoracle as po
 
     wl = WORKLOADS[args.workload]
-    rows, cols, res = wl["rows"], wl["cols"], wl["res"]
-    half_x, half_y = rows * res / 2, cols * res / 2
-    camd = synth.scaled_camera(wl["cam_scale"]) if wl["cam_scale"] != 1.0 else dict(synth.C3_CAMERA)
-    poses = synth.lawnmower_poses(wl["lines"], wl["per_line"], half_x, half_y, wl["agl"], seed=4)
-    n_frames = len(poses)
+    rows, cols, res, half_x, half_y, camd, poses = workload_inputs(wl)
+    do_dsm, do_ortho = wl["dsm"], wl["ortho"]
+    colored = bool(wl.get("colored", False))
+    batch = wl.get("batch", 0)
+    n_frames = len(poses) if do_ortho else 0
     sc = min(wl["cpu_stripe_cols"], cols)
     j0 = (cols - sc) // 2
     geom = po.make_geometry(rows, cols, res)
-    # points of the stripe + 3 m (largest retry threshold reaches 2.6 m), same density / terrain as the workload
-    y_hi = half_y - res * j0 + 3.0
-    y_lo = half_y - res * (j0 + sc) - 3.0
-    n_sample = int(round(wl["n_points"] * (y_hi - y_lo) / (2 * half_y)))
-    rng = np.random.Generator(np.random.PCG64(2))
-    xyz = np.empty((n_sample, 3))
-    xyz[:, 0] = rng.uniform(-half_x, half_x, n_sample)
-    xyz[:, 1] = rng.uniform(y_lo, y_hi, n_sample)
-    xyz[:, 2] = synth.terrain(xyz[:, 0], xyz[:, 1]) + rng.normal(0, 0.05, n_sample)
-    imgs = [synth.procedural_image(k, camd["width"], camd["height"]) for k in range(n_frames)]
+    xyz, n_sample = None, 0
+    if do_dsm:
+        # points of the stripe + 3 m (largest retry threshold reaches 2.6 m), same density / terrain as the workload
+        y_hi = half_y - res * j0 + 3.0
+        y_lo = half_y - res * (j0 + sc) - 3.0
+        n_sample = int(round(wl["n_points"] * (y_hi - y_lo) / (2 * half_y)))
+        rng = np.random.Generator(np.random.PCG64(2))
+        xyz = np.empty((n_sample, 3))
+        xyz[:, 0] = rng.uniform(-half_x, half_x, n_sample)
+        xyz[:, 1] = rng.uniform(y_lo, y_hi, n_sample)
+        xyz[:, 2] = synth.terrain(xyz[:, 0], xyz[:, 1]) + rng.normal(0, 0.05, n_sample)
+        if wl.get("holes"):
+            keep = np.ones(n_sample, bool)
+            for cx, cy, sx, sy in hole_rectangles(wl, half_x, half_y):
+                if cy + sy / 2 < y_lo or cy - sy / 2 > y_hi:
+                    continue
+                keep &= ~((np.abs(xyz[:, 0] - cx) < 0.5 * sx) & (np.abs(xyz[:, 1] - cy) < 0.5 * sy))
+            xyz = np.ascontiguousarray(xyz[keep])
+            n_sample = xyz.shape[0]
+    imgs = [synth.procedural_image(k, camd["width"], camd["height"], 3 if colored else 1) for k in range(n_frames)]
     cam = po.make_camera(**camd)
     use_refsrc = po.have_refsrc()   # the reference's own dsm.cc / ortho-backward-grid.cc compiled verbatim (oracle/_ref)
     use_ref = po.have_ref()
     threads = po.hardware_concurrency()
     k0, k1 = rows * j0, rows * (j0 + sc)
     sample_cells = k1 - k0
+    elev0 = synth.analytic_elevation(rows, cols, res) if (do_ortho and not do_dsm) else None
+    out_name = "colored_ortho" if colored else "ortho"
 
     def one():
-        layers = {"elevation": np.full((rows, cols), np.nan, np.float32, order="F"),
+        layers = {"elevation": np.full((rows, cols), np.nan, np.float32, order="F") if elev0 is None else elev0.copy(order="F"),
                   "elevation_angle": np.zeros((rows, cols), np.float32, order="F"),
                   "observation_index": np.full((rows, cols), np.nan, np.float32, order="F"),
-                  "ortho": np.full((rows, cols), 255.0, np.float32, order="F")}
+                  out_name: np.full((rows, cols), np.nan if colored else 255.0, np.float32, order="F")}
+        t_dsm = t_ortho = 0.0
         if use_refsrc:
             # dsm::Dsm(...).process() and ortho::OrthoBackwardGrid(...).process(), multi-threaded as the reference
-            # defaults (use_multi_threads = true, std::thread::hardware_concurrency() blocks); timed = the two
-            # process() calls (kd-tree build + both cell loops), constructors (one sample per cell) reported aside
-            st, sec = po.refsrc_dsm_process(geom, layers["elevation"], xyz, multi_thread=True, cell_range=(k0, k1))
-            assert st == 0, (st, po.refsrc_last_error())
-            st, osec = po.refsrc_ortho_process(geom, layers, cam, poses, imgs, multi_thread=True,
-                                               cell_range=(k0, k1))
-            assert st == 0, (st, po.refsrc_last_error())
-            return float(sec[1] + osec[1]), np.array([sec[0] + osec[0], sec[1]]), float(osec[1])
+            # defaults (use_multi_threads = true, std::thread::hardware_concurrency() blocks); timed = the process()
+            # calls (kd-tree build + cell loops); constructors (one sample per cell) are not counted
+            if do_dsm:
+                st, sec = po.refsrc_dsm_process(geom, layers["elevation"], xyz, multi_thread=True, cell_range=(k0, k1))
+                assert st == 0, (st, po.refsrc_last_error())
+                t_dsm = float(sec[1])
+            if do_ortho:
+                for b0 in range(0, n_frames, batch or n_frames):
+                    b1 = b0 + (batch or n_frames)
+                    st, osec = po.refsrc_ortho_process(geom, layers, cam, poses[b0:b1], imgs[b0:b1], colored=colored,
+                                                       multi_thread=True, cell_range=(k0, k1))
+                    assert st == 0, (st, po.refsrc_last_error())
+                    t_ortho += float(osec[1])
+            return t_dsm + t_ortho, t_dsm, t_ortho
         t0 = time.perf_counter()
-        st, _, _, sec = po.dsm_process(geom, layers["elevation"], xyz, num_threads=0, cell_range=(k0, k1),
-                                       use_ref=use_ref)
-        assert st == 0, st
-        st, osec = po.ortho_process(geom, layers, cam, poses, imgs, num_threads=0, cell_range=(k0, k1))
-        assert st == 0, st
-        return time.perf_counter() - t0, sec, osec
+        if do_dsm:
+            st, _, _, sec = po.dsm_process(geom, layers["elevation"], xyz, num_threads=0, cell_range=(k0, k1), use_ref=use_ref)
+            assert st == 0, st
+        t1 = time.perf_counter()
+        if do_ortho:
+            for b0 in range(0, n_frames, batch or n_frames):
+                b1 = b0 + (batch or n_frames)
+                st, osec = po.ortho_process(geom, layers, cam, poses[b0:b1], imgs[b0:b1], num_threads=0, cell_range=(k0, k1),
+                                            **({"colored": True} if colored else {}))
+                assert st == 0, st
+        t2 = time.perf_counter()
+        return t2 - t0, t1 - t0, t2 - t1
 
     for _ in range(warmup):
         one()
     times, dsm_secs, ortho_secs = [], [], []
     for _ in range(max(1, steps)):
-        t, sec, osec = one()
+        t, td, to = one()
         times.append(t)
-        dsm_secs.append(sec.tolist())
-        ortho_secs.append(osec)
+        dsm_secs.append(td)
+        ortho_secs.append(to)
     t_step = float(np.mean(times))
     value = sample_cells / t_step
-    if use_refsrc:
-        kind = "reference"
-        sample = ("%d-column stripe (%d cells of %d) at the map centre, %d points within stripe+3 m, all %d frames; "
-                  "the reference's own dsm.cc + ortho-backward-grid.cc (+ nanoflann.hpp, utils::parFor) compiled "
-                  "verbatim into oracle/_ref against stand-in third-party headers, multi-threaded on %d threads; "
-                  "timed = Dsm::process %.2fs (kd-tree + cell loop) + OrthoBackwardGrid::process %.2fs; "
-                  "constructors (one sample per cell) %.2fs not counted"
-                  % (sc, sample_cells, rows * cols, n_sample, n_frames, threads, dsm_secs[-1][1], ortho_secs[-1],
-                     dsm_secs[-1][0]))
-    else:
-        kind = "port"
-        sample = ("%d-column stripe (%d cells of %d) at the map centre, %d points within stripe+3 m, all %d "
-                  "frames; DSM = %s; ortho = restated loop; parFor over %d threads; kd-tree build %.2fs + cell loop "
-                  "%.2fs, ortho loop %.2fs"
-                  % (sc, sample_cells, rows * cols, n_sample, n_frames,
-                     "reference's vendored nanoflann.hpp compiled verbatim + restated cell loop (oracle/_ref)"
-                     if use_ref else "dependency-free restatement (oracle/)", threads, dsm_secs[-1][0],
-                     dsm_secs[-1][1], ortho_secs[-1]))
-    base = {"value": value, "unit": "cells/s", "cores": threads, "kind": kind, "sample": sample}
+    kind = "reference" if use_refsrc else "port"
+    sample = ("EXTRAPOLATED from a %d-column stripe (%d cells of %d = %.3f of the job) at the map centre%s%s; %s, "
+              "multi-threaded on %d host threads; timed = Dsm::process %.2f s + OrthoBackwardGrid::process %.2f s "
+              "(constructors not counted)"
+              % (sc, sample_cells, rows * cols, sample_cells / float(rows * cols),
+                 (", %d points within stripe+3 m" % n_sample) if do_dsm else "",
+                 (", all %d frames%s" % (n_frames, " in batches of %d" % batch if batch else "")) if do_ortho else "",
+                 "the reference's own dsm.cc + ortho-backward-grid.cc (+ nanoflann.hpp, utils::parFor) compiled verbatim into "
+                 "oracle/_ref against stand-in third-party headers" if use_refsrc else
+                 "restated port (oracle/; oracle/_ref not built)", threads, float(np.mean(dsm_secs)),
+                 float(np.mean(ortho_secs))))
+    base = {"value": value, "unit": "cells/s", "cores": threads, "kind": kind, "sample": sample, "extrapolated": True,
+            "sample_fraction": sample_cells / float(rows * cols)}
     return {"cpu_baseline": base, "ms_per_step": t_step * 1e3, "value": value,
             "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res),
-                       "points": int(wl["n_points"]), "frames": "%dx %dx%d gray" % (n_frames, camd["width"],
-                                                                                  camd["height"]),
+                       "points": int(wl["n_points"]),
+                       "frames": ("%dx %dx%d %s" % (n_frames, camd["width"], camd["height"], "BGR" if colored else "gray"))
+                       if do_ortho else "none",
                        "interpolation_radius": 1}}
 
 

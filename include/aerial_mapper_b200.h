@@ -141,6 +141,9 @@ int amb_init_layers(amb_ctx* ctx);
  * caller offsets a full-map pointer by rows*col_begin; rows*(col_end-col_begin) floats are moved. */
 int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab);
 int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab);
+/* Set a layer slab from DEVICE memory valid on the context's device (rows*(col_end-col_begin) floats, e.g. an elevation
+ * layer produced by another stage that never leaves HBM).  Asynchronous on the context's stream. */
+int amb_upload_layer_device(amb_ctx* ctx, int layer, const float* device_slab);
 /* Same, asynchronous: the copy is ordered after the work enqueued so far and runs on a second stream, so it
  * overlaps later kernels and host->device copies (use page-locked host memory); amb_sync() completes it. */
 int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab);
