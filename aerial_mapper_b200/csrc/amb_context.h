@@ -173,6 +173,8 @@ struct amb_ctx {
   // multi-GPU (amb_comm.cu): NCCL communicator this context is a member of, and the halo buffers of the exchange step
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  std::vector<int32_t> comm_stripes;   // [2 * nranks]: col_begin, col_end of every member (gathered by amb_comm_init)
+  int halo_exchange_mode = 0;          // 0 auto, 1 all-gather, 2 neighbours (amb_comm_set_exchange)
   amb::DeviceBuffer halo_send, halo_recv;
   int dsm_precision = AMB_DSM_F32;  // amb_dsm_set_precision: arithmetic of the tile gather's weights and sums
   bool dsm_debug_valid = false;

@@ -28,7 +28,8 @@ Multi-GPU (torchrun, one rank per GPU): the map is sharded by contiguous column 
 sharded the same way (every rank holds the points of its own stripe, with global ids); frames are resident on every rank
 ("images broadcast once", outside the timed region).  Per step each rank runs amb_dsm_process_sharded_device — halo
 compaction, ONE ncclAllGather of the border halos inside the library, binning, gather — then the orthomosaic of its
-stripe; the result layers stay sharded.  Strong scaling: the job is fixed.  Before timing, every rank also evaluates
+stripe (the halos travel by ncclSend/ncclRecv to the two adjacent ranks when every stripe is wider than the reach,
+else by one ncclAllGather); the result layers stay sharded.  Strong scaling: the job is fixed.  Before timing, every rank also evaluates
 the UNDIVIDED map once and compares its stripe bit for bit (`sharded_equals_undivided`); `checksum` is the sum of the
 result layers' bit patterns over all ranks (equal for every N).
 """
@@ -318,8 +319,10 @@ def run_ours(args):
     local_xyz = local_ids = None
     halo_cap = 0
     n_local = n_points
+    exchange_mode = int(os.environ.get("AMB_HALO_EXCHANGE", "0"))   # 0 auto, 1 all-gather, 2 neighbours
     if world > 1:
         sharding.init_comm(ctx, dist, rank, world, device)
+        amb.check(amb.lib().amb_comm_set_exchange(ctx, exchange_mode), ctx)
         if do_dsm:
             y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
             reach = amb.lib().amb_dsm_halo_reach(C.byref(gm.geometry), 1)
@@ -521,8 +524,12 @@ def run_ours(args):
                       "frames": ("%dx %dx%d %s" % (n_frames, W, H, "BGR" if colored else "gray")) if do_ortho else "none",
                       "frame_batches": (n_frames // batch) if batch else (1 if do_ortho else 0),
                       "interpolation_radius": 1, "dsm_precision": lib_prec if do_dsm else None,
-                      "sharding": ("column stripes x%d; cloud sharded by stripe; 1 ncclAllGather of border halos per step "
-                                   "inside the library; layers stay sharded" % world) if world > 1 else "single GPU",
+                      "sharding": ("column stripes x%d; cloud sharded by stripe; border halos exchanged inside the library on "
+                                   "its own stream (%s); layers stay sharded"
+                                   % (world, {0: "auto: ncclSend/ncclRecv with the two adjacent ranks, one ncclAllGather for "
+                                                 "stripes narrower than the reach", 1: "one ncclAllGather",
+                                              2: "ncclSend/ncclRecv with the two adjacent ranks"}[exchange_mode]))
+                      if world > 1 else "single GPU",
                       "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W * channels) / 1e9),
                       "timed_region": "K steps enqueued back to back, one synchronisation at the end"},
            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline,
@@ -581,6 +588,7 @@ def run_e2e(args, torch, amb, sharding, C, dist, device, local_rank, rank, world
     gmh.set_mirrors(result_names)   # result layers stream back to the (pinned) host map as they become final
     if world > 1:
         sharding.init_comm(ctx_h, dist, rank, world, device)
+        amb.check(amb.lib().amb_comm_set_exchange(ctx_h, int(os.environ.get("AMB_HALO_EXCHANGE", "0"))), ctx_h)
         amb.check(amb.lib().amb_dsm_set_density_hint(ctx_h, n_points / float(rows * cols)), ctx_h)
     dsm_h = amb.Dsm(amb.DsmSettings(), gmh)
     ortho_h = amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(colored_ortho=colored), gmh) if do_ortho else None

@@ -216,6 +216,10 @@ int amb_dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_id
 int amb_comm_unique_id(void* id128);
 int amb_comm_init(amb_ctx* ctx, int rank, int nranks, const void* id128);
 int amb_comm_destroy(amb_ctx* ctx);
+/* How amb_dsm_process_sharded* exchanges the border halos: 0 (default) = automatic — two ncclSend/ncclRecv pairs with the
+ * adjacent ranks when the stripes are consecutive and each at least amb_dsm_halo_reach wide, else one ncclAllGather;
+ * 1 = always the all-gather; 2 = always neighbours (the caller guarantees the condition).  Same value on every rank. */
+int amb_comm_set_exchange(amb_ctx* ctx, int mode);
 int amb_comm_size(const amb_ctx* ctx);
 int amb_comm_rank(const amb_ctx* ctx);
 /* Dsm::process on a cloud that arrives sharded by stripe, the exchange included: this rank's points (device memory, global
