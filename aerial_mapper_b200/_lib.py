@@ -120,7 +120,7 @@ SYMBOLS = {
 
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".h", ".cuh", ".inc"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cc", ".h", ".cuh", ".inc", "Makefile"))]
     srcs.append(os.path.join(_HERE, "..", "include", "aerial_mapper_b200.h"))
     need = force or not os.path.exists(LIB_PATH)
     if not need:

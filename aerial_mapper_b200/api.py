@@ -161,8 +161,8 @@ class GridMap(object):
         """Register the host layers as mirrors (amb_set_host_mirror): process() streams every result layer back as
         soon as it is final, overlapping later stages; sync() completes the copies.  Use pinned layers."""
         ctx = self.context()
-        # opt-in one-byte transport of `ortho` / `observation_index` (amb_set_host_mirror_compact)
-        compact = os.environ.get("AMB_COMPACT_MIRRORS", "0") not in ("", "0")
+        # one-byte transport of `ortho` / `observation_index` (amb_set_host_mirror_compact; AMB_COMPACT_MIRRORS=0 turns it off)
+        compact = os.environ.get("AMB_COMPACT_MIRRORS", "1") not in ("", "0")   # default on (exact-bits transport)
         for name in names:
             slab = self._slab(name)
             ptr = slab.ctypes.data_as(C.c_void_p) if enable else None
@@ -255,8 +255,8 @@ class Dsm(object):
         # float32 weights and sums, neighbour sets exact; the environment variable AMB_DSM_PRECISION=f64|f32, read by
         # the library itself, overrides that default process-wide — how the tests run both), or "f32" / "f64"
         self.precision = None
-        # opt-in chunked evaluation + early mirroring of finished columns (amb_dsm_set_stream_chunks); 1 = off
-        self.stream_chunks = max(1, int(os.environ.get("AMB_DSM_STREAM_CHUNKS", "1") or 1))
+        # chunked evaluation + early mirroring of finished columns (amb_dsm_set_stream_chunks); 1 = off, default 4
+        self.stream_chunks = max(1, int(os.environ.get("AMB_DSM_STREAM_CHUNKS", "4") or 4))
 
     def process(self, point_cloud, map):
         """point_cloud: float64 [n, 3] (the AoS layout of std::vector<Eigen::Vector3d>).  Mutates map['elevation']."""

@@ -42,12 +42,8 @@ int enqueue_layer_download(amb_ctx* ctx, int layer, float* host_slab) {
 int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer] || col1 <= col0)
     return AMB_OK;
-  if (ctx->compact[layer].enabled) {
-    // column chunks always travel as float32; expander threads of an earlier compact round may still be writing the mirror
-    for (std::thread& t : ctx->compact[layer].workers)
-      if (t.joinable()) t.join();
-    ctx->compact[layer].workers.clear();
-  }
+  // column chunks always travel as float32; the expander pool may still be widening an earlier compact round into the mirror
+  if (ctx->compact[layer].enabled) wait_compact_layer(ctx, layer);
   const size_t off = static_cast<size_t>(ctx->geom.rows) * static_cast<size_t>(col0);
   const size_t cnt = static_cast<size_t>(ctx->geom.rows) * static_cast<size_t>(col1 - col0);
   AMB_CUDA(ctx, cudaEventRecord(ctx->copy_done[0], ctx->stream));
@@ -63,7 +59,8 @@ int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1) {
 
 int mirror_layer(amb_ctx* ctx, int layer) {
   if (layer < 0 || layer >= AMB_NUM_LAYERS || !ctx->host_mirror[layer] || !ctx->layers[layer]) return AMB_OK;
-  if (ctx->compact[layer].enabled) return mirror_layer_compact(ctx, layer);  // opt-in (amb_set_host_mirror_compact)
+  if (ctx->compact[layer].enabled && (layer == AMB_LAYER_ORTHO || layer == AMB_LAYER_OBSERVATION_INDEX))
+    return mirror_layer_compact(ctx, layer);  // one byte per cell when every value has a code (amb_set_host_mirror_compact)
   return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
 }
 

@@ -107,8 +107,7 @@ __device__ __forceinline__ void halo_append(bool take, int lane, unsigned char* 
 __global__ void __launch_bounds__(256) dsm_halo_records_kernel(const double* __restrict__ xyz,
                                                                const unsigned long long* __restrict__ ids, size_t n,
                                                                double y_lo, double y_hi, double reach, double shift_y,
-                                                               unsigned char* __restrict__ seg_up,
-                                                               unsigned char* __restrict__ seg_down, bool split,
+                                                               unsigned char* seg_up, unsigned char* seg_down, bool split,
                                                                unsigned int capacity) {
   const int lane = threadIdx.x & 31;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;

@@ -111,7 +111,8 @@ enum CounterSlot {
 
 // Narrow transport of a small-integer result layer to its host mirror (mirror_compact.cu)
 struct CompactMirror {
-  bool enabled = false;
+  bool enabled = true;                // (ortho / observation_index mirrors) amb_set_host_mirror_compact(.., 0) turns it off;
+                                      // measured 63.2 -> 56.5 ms end to end at joint_10k
   std::atomic<bool> failed{false};    // an expander thread could not wait for its chunk: reported by amb_sync, which then
                                       // re-downloads the layer as float32
   DeviceBuffer codes;                 // one byte per slab cell
@@ -119,7 +120,7 @@ struct CompactMirror {
   size_t host_bytes = 0;
   unsigned int* host_flag = nullptr;  // pinned + mapped: set by the pack kernel when a value has no code
   std::vector<cudaEvent_t> chunk_events;
-  std::vector<std::thread> workers;   // expander threads of the round in flight
+  std::atomic<int> jobs_in_flight{0}; // chunks of the current round still being widened by the expander pool
 };
 
 // The neighbours' border halos as delivered by the all-gather (amb_comm.cu): nranks segments of seg_bytes, each a 32-byte
@@ -169,7 +170,8 @@ struct amb_ctx {
   amb::DeviceBuffer dbg_level;    // int8 per slab cell
   double dsm_density_hint = 0.0;  // points per cell of the whole cloud (0: derive from the points passed)
   bool dsm_debug = false;
-  int dsm_stream_chunks = 1;  // opt-in (> 1): gather + fill in column chunks, each chunk's result mirrored to the host at once
+  int dsm_stream_chunks = 4;  // (> 1, only with a host mirror of the output layer) gather + fill in column chunks, each chunk's
+                              // result mirrored to the host at once: measured 63.2 -> 59.5 ms end to end at joint_10k
   // multi-GPU (amb_comm.cu): NCCL communicator this context is a member of, and the halo buffers of the exchange step
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
@@ -220,6 +222,7 @@ int mirror_layer_columns(amb_ctx* ctx, int layer, int col0, int col1);  // slab-
 // mirror_compact.cu
 int mirror_layer_compact(amb_ctx* ctx, int layer);
 int join_compact_mirrors(amb_ctx* ctx);         // AMB_ERR_CUDA if an expander failed (the layer was re-downloaded as float32)
+void wait_compact_layer(amb_ctx* ctx, int layer);  // the expander pool has finished this layer's round
 void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the registered host mirror, if any
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu

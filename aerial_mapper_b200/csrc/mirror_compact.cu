@@ -12,12 +12,16 @@
 //   chunked D2H         of the codes on the copy stream, one event per chunk
 //   expander threads    wait for their chunks' events and write the float32 values into the caller's mirror
 // amb_sync (and a later compact mirror of the same layer) join the threads.
+#include <condition_variable>
+#include <deque>
 #include <exception>
+#include <mutex>
 #include <thread>
 
 #include "amb_context.h"
 
 namespace amb {
+void expand_codes(const uint8_t* src, float* dst, size_t n, int nan_code);  // mirror_expand.cc
 namespace {
 
 #ifdef AMB_CUDA_EMU  // tests/emu: small chunks so that small maps exercise the multi-chunk / ragged-end logic
@@ -25,7 +29,7 @@ constexpr size_t kChunkCells = 3000;
 #else
 constexpr size_t kChunkCells = 4u << 20;  // 4 M cells: 4 MB of codes, 16 MB of float32
 #endif
-constexpr int kExpanders = 8;             // host threads per layer in flight
+constexpr int kExpanders = 16;            // host threads widening codes (one pool per process)
 
 // nan_code < 0: the layer has no NaN code (every byte value is a number)
 __global__ void __launch_bounds__(256) pack_codes_kernel(const float* __restrict__ layer, uint8_t* __restrict__ codes,
@@ -57,43 +61,88 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(const float* __restrict
   if (any_bad) *bad = 1u;  // benign race: every writer stores the same value
 }
 
-void expand_chunks(amb_ctx* ctx, int layer, int first, int stride, int n_chunks, size_t cells, int nan_code) {
-  cudaSetDevice(ctx->device);
-  CompactMirror& cm = ctx->compact[layer];
-  float* out = ctx->host_mirror[layer];
-  float nanv;
-  {
-    const unsigned int qnan = 0x7fc00000u;  // the bit pattern pack_codes_kernel accepted
-    std::memcpy(&nanv, &qnan, sizeof(nanv));
+// One expander pool per process: kExpanders threads, started on first use, fed (layer round, chunk) jobs.  A job waits for
+// its chunk's copy event and widens the chunk with expand_codes (mirror_expand.cc: AVX2, streaming stores).
+struct ExpandJob {
+  amb_ctx* ctx;
+  int layer, chunk;
+  size_t lo, hi;
+  int nan_code;
+};
+
+class ExpanderPool {
+ public:
+  static ExpanderPool& instance() {
+    // intentionally never destroyed: the detached workers block on its condition variable until the process ends
+    static ExpanderPool* pool = new ExpanderPool;
+    return *pool;
   }
-  for (int c = first; c < n_chunks; c += stride) {
-    if (cudaEventSynchronize(cm.chunk_events[c]) != cudaSuccess) {
-      cm.failed = true;
-      return;
+  // false if the workers could not be started (the caller then falls back to the float32 download)
+  bool submit(const ExpandJob& job) {
+    std::unique_lock<std::mutex> lock(mu_);
+    if (!started_ && !start_locked()) return false;
+    queue_.push_back(job);
+    ++job.ctx->compact[job.layer].jobs_in_flight;
+    lock.unlock();
+    cv_.notify_one();
+    return true;
+  }
+  void wait_layer(amb_ctx* ctx, int layer) {
+    std::unique_lock<std::mutex> lock(mu_);
+    done_cv_.wait(lock, [&] { return ctx->compact[layer].jobs_in_flight == 0; });
+  }
+
+ private:
+  bool start_locked() {
+    try {
+      for (int t = 0; t < kExpanders; ++t) std::thread([this] { run(); }).detach();
+    } catch (const std::exception&) {
+      return false;
     }
-    const size_t lo = static_cast<size_t>(c) * kChunkCells, hi = lo + kChunkCells < cells ? lo + kChunkCells : cells;
-    const uint8_t* src = cm.host_codes;
-    if (nan_code >= 0) {
-      for (size_t k = lo; k < hi; ++k) out[k] = src[k] == nan_code ? nanv : static_cast<float>(src[k]);
-    } else {
-      for (size_t k = lo; k < hi; ++k) out[k] = static_cast<float>(src[k]);
+    started_ = true;
+    return true;
+  }
+  void run() {
+    for (;;) {
+      ExpandJob job;
+      {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_.wait(lock, [&] { return !queue_.empty(); });
+        job = queue_.front();
+        queue_.pop_front();
+      }
+      CompactMirror& cm = job.ctx->compact[job.layer];
+      cudaSetDevice(job.ctx->device);
+      if (cudaEventSynchronize(cm.chunk_events[job.chunk]) != cudaSuccess) {
+        cm.failed = true;
+      } else {
+        expand_codes(cm.host_codes + job.lo, job.ctx->host_mirror[job.layer] + job.lo, job.hi - job.lo, job.nan_code);
+      }
+      {
+        std::lock_guard<std::mutex> lock(mu_);
+        --cm.jobs_in_flight;
+      }
+      done_cv_.notify_all();
     }
   }
-}
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::deque<ExpandJob> queue_;
+  bool started_ = false;
+};
 
 }  // namespace
 
-static void join_layer(CompactMirror& cm) {
-  for (std::thread& t : cm.workers)
-    if (t.joinable()) t.join();
-  cm.workers.clear();
+
+void wait_compact_layer(amb_ctx* ctx, int layer) {
+  if (ctx->compact[layer].jobs_in_flight.load() != 0) ExpanderPool::instance().wait_layer(ctx, layer);
 }
 
 int join_compact_mirrors(amb_ctx* ctx) {
   int status = AMB_OK;
   for (int l = 0; l < AMB_NUM_LAYERS; ++l) {
     CompactMirror& cm = ctx->compact[l];
-    join_layer(cm);
+    wait_compact_layer(ctx, l);
     if (cm.failed.exchange(false)) {
       // an expander gave up (its chunk event could not be waited for): the mirror is only partly widened.  Repair it with
       // a plain synchronous float32 download and tell the caller.
@@ -109,7 +158,7 @@ int join_compact_mirrors(amb_ctx* ctx) {
 void release_compact_mirrors(amb_ctx* ctx) {
   for (int l = 0; l < AMB_NUM_LAYERS; ++l) {
     CompactMirror& cm = ctx->compact[l];
-    join_layer(cm);
+    wait_compact_layer(ctx, l);
     cm.codes.release();
     if (cm.host_codes) cudaFreeHost(cm.host_codes);
     if (cm.host_flag) cudaFreeHost(cm.host_flag);
@@ -127,7 +176,7 @@ int mirror_layer_compact(amb_ctx* ctx, int layer) {
   CompactMirror& cm = ctx->compact[layer];
   const int nan_code = layer == AMB_LAYER_OBSERVATION_INDEX ? 255 : -1;
   const size_t cells = ctx->slab_cells();
-  join_layer(cm);  // the previous round's expansion of this layer
+  wait_compact_layer(ctx, layer);  // the previous round's expansion of this layer
   AMB_CUDA(ctx, cm.codes.reserve(cells));
   if (cm.host_bytes < cells) {
     if (cm.host_codes) cudaFreeHost(cm.host_codes);
@@ -160,13 +209,13 @@ int mirror_layer_compact(amb_ctx* ctx, int layer) {
                                   ctx->copy_stream));
     AMB_CUDA(ctx, cudaEventRecord(cm.chunk_events[c], ctx->copy_stream));
   }
-  const int n_workers = n_chunks < kExpanders ? n_chunks : kExpanders;
-  try {
-    for (int t = 0; t < n_workers; ++t)
-      cm.workers.emplace_back(expand_chunks, ctx, layer, t, n_workers, n_chunks, cells, nan_code);
-  } catch (const std::exception&) {  // thread creation failed: nothing may escape the extern "C" boundary
-    join_layer(cm);
-    return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);  // overwrites whatever the started workers wrote
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t lo = static_cast<size_t>(c) * kChunkCells, hi = lo + kChunkCells < cells ? lo + kChunkCells : cells;
+    if (!ExpanderPool::instance().submit(ExpandJob{ctx, layer, c, lo, hi, nan_code})) {
+      // no worker threads: wait for what was queued, then the plain float32 transport (overwrites the partial result)
+      wait_compact_layer(ctx, layer);
+      return enqueue_layer_download(ctx, layer, ctx->host_mirror[layer]);
+    }
   }
   return AMB_OK;
 }

@@ -153,9 +153,9 @@ int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab);
  * uploaded; the ortho layer after the texel gather), on a second stream.  amb_sync() completes the copies.  This is
  * the host-authoritative model of the reference (process() mutates the caller's map) without serialising PCIe. */
 int amb_set_host_mirror(amb_ctx* ctx, int layer, float* host_slab);
-/* Opt-in narrow transport for the mirrors of AMB_LAYER_ORTHO and AMB_LAYER_OBSERVATION_INDEX (others:
- * AMB_ERR_INVALID_ARGUMENT): the layer crosses PCIe as one byte per cell and host threads inside the library widen it to
- * the float32 values of the mirror (amb_sync waits for them).  Whenever a value has no one-byte code — anything but the
+/* Narrow transport for the mirrors of AMB_LAYER_ORTHO and AMB_LAYER_OBSERVATION_INDEX (others: AMB_ERR_INVALID_ARGUMENT),
+ * on by default, enable = 0 turns it off: the layer crosses PCIe as one byte per cell and a pool of host threads inside
+ * the library widens it to the float32 values of the mirror (amb_sync waits for them).  Whenever a value has no one-byte code — anything but the
  * integers 0..255 (`ortho`) / 0..254 and the canonical NaN (`observation_index`) — the layer travels as float32 as before:
  * the mirror always receives the layer's exact bits. */
 int amb_set_host_mirror_compact(amb_ctx* ctx, int layer, int enable);
@@ -192,7 +192,7 @@ int amb_dsm_set_density_hint(amb_ctx* ctx, double points_per_cell);
  *   AMB_DSM_F64: everything in double in the reference's operation order (<= 1 float32 ulp by construction; ~2x slower). */
 typedef enum amb_dsm_precision { AMB_DSM_F64 = 0, AMB_DSM_F32 = 1 } amb_dsm_precision;
 int amb_dsm_set_precision(amb_ctx* ctx, int precision);
-/* Opt-in (default 1 = off): with a host mirror registered for the output layer (amb_set_host_mirror), evaluate the map's
+/* Default 4 (1 = off): with a host mirror registered for the output layer (amb_set_host_mirror), evaluate the map's
  * tile columns in `chunks` groups and start each group's download as soon as it is final, so that the layer's trip to the
  * host overlaps the evaluation of the remaining groups.  Same launches restricted to tile-column ranges: same output bits. */
 int amb_dsm_set_stream_chunks(amb_ctx* ctx, int chunks);

@@ -111,7 +111,7 @@ def _emu_worker(rank, world, port, tmp):
     ids = torch.arange(xyz.shape[0], dtype=torch.int64)
     y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
     m = sharding.owner_mask(xyz[:, 1], y_lo, y_hi, rank, world)         # this rank's share of the cloud
-    hx = sharding.HaloExchange(torch, world, rank, 8000, xyz[m], ids[m], torch.device("cpu"))
+    hx = sharding.HaloExchange(torch, world, rank, 40000, xyz[m], ids[m], torch.device("cpu"))
     reach = amb.lib().amb_dsm_halo_reach(C.byref(gm.geometry), 1)
     amb.check(amb.lib().amb_dsm_set_density_hint(gm.context(), xyz.shape[0] / float(rows * cols)), gm.context())
     hx.extract(gm.context(), y_lo, y_hi, reach)
