@@ -75,7 +75,89 @@ struct OrthoArgs {
   double nui_lo, nui_hi, nvi_lo, nvi_hi;  // sqrt(1 + bound^2)
   double dom_margin;                      // rad
   double dom_theta_in;                    // equidistant: every ray with angle-to-axis below this is imaged (else unused)
+  // --- exact re-evaluation (appended) ---
+  const double* exact_data;               // device array [n_frames][8]: inverse(T_G_C) as the reference forms it —
+                                          // conjugate quaternion (w, x, y, z), translation -(q^-1).rotate(t), pad
 };
+
+// Guard bands of the fused fast path.  Its camera coordinates come from a pre-multiplied rotation matrix with FMA
+// contraction and a <= 1 ulp reciprocal; the reference (minkindr / Eigen / aslam_cv2, see exact_* below) rotates by the
+// quaternion formula and divides.  Both carry ~1e-16 relative rounding: keypoints agree to ~1e-12 px (|k| <= 1e4 px),
+// camera z to ~1e-12 m.  A decision closer to its boundary than the guard is re-made with the reference's own
+// operation sequence, un-contracted, so visibility, winner and pixel are the reference's by construction.
+constexpr double kGuardPx = 1e-9;   // keypoint vs raster edge / half-integer
+constexpr double kGuardZ = 1e-6;    // camera z vs kMinimumDepth (1e-10): anything that close to the camera plane goes exact
+
+// ---- the reference's arithmetic, operation by operation (restated third-party code: oracle/thirdparty_math.h cites the
+// upstream sources; parity tests compare with it), no FMA contraction, IEEE division ----
+// Eigen QuaternionBase::_transformVector: uv = q.vec x v; uv += uv; v + q.w*uv + q.vec x uv
+__device__ __forceinline__ void exact_quat_rotate(double qw, double qx, double qy, double qz, double vx, double vy,
+                                                  double vz, double* rx, double* ry, double* rz) {
+  double ux = __dadd_rn(__dmul_rn(qy, vz), -__dmul_rn(qz, vy));
+  double uy = __dadd_rn(__dmul_rn(qz, vx), -__dmul_rn(qx, vz));
+  double uz = __dadd_rn(__dmul_rn(qx, vy), -__dmul_rn(qy, vx));
+  ux = __dadd_rn(ux, ux);
+  uy = __dadd_rn(uy, uy);
+  uz = __dadd_rn(uz, uz);
+  const double cx = __dadd_rn(__dmul_rn(qy, uz), -__dmul_rn(qz, uy));
+  const double cy = __dadd_rn(__dmul_rn(qz, ux), -__dmul_rn(qx, uz));
+  const double cz = __dadd_rn(__dmul_rn(qx, uy), -__dmul_rn(qy, ux));
+  *rx = __dadd_rn(__dadd_rn(vx, __dmul_rn(qw, ux)), cx);
+  *ry = __dadd_rn(__dadd_rn(vy, __dmul_rn(qw, uy)), cy);
+  *rz = __dadd_rn(__dadd_rn(vz, __dmul_rn(qw, uz)), cz);
+}
+
+// T_G_C.inverse().transform(landmark) (ortho-backward-grid.cc:157-158): q^-1.rotate(p) + t_inv
+__device__ __noinline__ void exact_to_camera(const OrthoArgs& a, int f, double X, double Y, double Z, double* xc,
+                                                double* yc, double* zc) {
+  const double* e = a.exact_data + 8 * static_cast<size_t>(f);
+  double rx, ry, rz;
+  exact_quat_rotate(__ldg(e + 0), __ldg(e + 1), __ldg(e + 2), __ldg(e + 3), X, Y, Z, &rx, &ry, &rz);
+  *xc = __dadd_rn(rx, __ldg(e + 4));
+  *yc = __dadd_rn(ry, __ldg(e + 5));
+  *zc = __dadd_rn(rz, __ldg(e + 6));
+}
+
+// aslam::PinholeCamera::project3Functional + the reference's keypoint_visible predicate (:159-171)
+template <int DIST>
+__device__ __noinline__ bool exact_project(const OrthoArgs& a, double x, double y, double z, double* kx, double* ky) {
+  const double rz = __ddiv_rn(1.0, z);
+  double u = __dmul_rn(x, rz);
+  double v = __dmul_rn(y, rz);
+  if (DIST == AMB_DIST_RADTAN) {
+    const double mx2 = __dmul_rn(u, u), my2 = __dmul_rn(v, v), mxy = __dmul_rn(u, v);
+    const double rho2 = __dadd_rn(mx2, my2);
+    const double rad = __dadd_rn(__dmul_rn(a.d0, rho2), __dmul_rn(__dmul_rn(a.d1, rho2), rho2));
+    // x += x*rad + 2*p1*mxy + p2*(rho2 + 2*mx2)   (left to right)
+    const double ax = __dadd_rn(__dadd_rn(__dmul_rn(u, rad), __dmul_rn(__dmul_rn(2.0, a.d2), mxy)),
+                                __dmul_rn(a.d3, __dadd_rn(rho2, __dmul_rn(2.0, mx2))));
+    const double ay = __dadd_rn(__dadd_rn(__dmul_rn(v, rad), __dmul_rn(__dmul_rn(2.0, a.d3), mxy)),
+                                __dmul_rn(a.d2, __dadd_rn(rho2, __dmul_rn(2.0, my2))));
+    u = __dadd_rn(u, ax);
+    v = __dadd_rn(v, ay);
+  } else if (DIST == AMB_DIST_EQUIDISTANT) {
+    const double r = sqrt(__dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v)));
+    if (r > 1e-8) {
+      const double th = atan(r);
+      const double th2 = __dmul_rn(th, th), th4 = __dmul_rn(th2, th2), th6 = __dmul_rn(th4, th2), th8 = __dmul_rn(th4, th4);
+      const double poly = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(1.0, __dmul_rn(a.d0, th2)), __dmul_rn(a.d1, th4)),
+                                              __dmul_rn(a.d2, th6)), __dmul_rn(a.d3, th8));
+      const double s = __ddiv_rn(__dmul_rn(th, poly), r);
+      u = __dmul_rn(u, s);
+      v = __dmul_rn(v, s);
+    }
+  }
+  *kx = __dadd_rn(__dmul_rn(a.fu, u), a.cu);
+  *ky = __dadd_rn(__dmul_rn(a.fv, v), a.cv);
+  return (*kx >= 0.0) && (*ky >= 0.0) && (*kx < static_cast<double>(a.width)) &&
+         (*ky < static_cast<double>(a.height)) && (z > 1e-10);
+}
+
+__device__ __noinline__ double exact_observation_angle(double xc, double yc, double zc) {
+  // u.norm() (:175) = sqrt(x*x + y*y + z*z), then asin(fabs(u(2)) / norm_u) (:177)
+  const double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(xc, xc), __dmul_rn(yc, yc)), __dmul_rn(zc, zc)));
+  return asin(__ddiv_rn(fabs(zc), n));
+}
 
 // Reciprocal of a positive normal double to ~1 ulp: MUFU.RCP64H seed + one cubic correction step.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -359,11 +441,12 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   // per-call tables live in pinned staging (see HostStage); the previous call's copies must have left it
   if (!ctx->stage_event) AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_event, cudaEventDisableTiming));
   AMB_CUDA(ctx, cudaEventSynchronize(ctx->stage_event));
-  AMB_CUDA(ctx, ctx->stage.reserve(n * (sizeof(FrameConst) + 12 * sizeof(double) + 8 * sizeof(int) +
+  AMB_CUDA(ctx, ctx->stage.reserve(n * (sizeof(FrameConst) + 20 * sizeof(double) + 8 * sizeof(int) +
                                         sizeof(FrameRect) + sizeof(uint8_t*)) + 1024));
   ctx->stage.used = 0;
   FrameConst* fcs = ctx->stage.take<FrameConst>(n);
   double* cull = ctx->stage.take<double>(12 * n);
+  double* exact = ctx->stage.take<double>(8 * n);
   for (size_t f = 0; f < n; ++f) {
     const double* p = T_G_B + 7 * f;
     const Quat q_G_B = {p[3], p[4], p[5], p[6]};
@@ -383,6 +466,10 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     double* cf = &cull[12 * f];
     cf[0] = t.x; cf[1] = t.y; cf[2] = t.z;
     for (int k = 0; k < 9; ++k) cf[3 + k] = fc.m[k];
+    // inverse(T_G_C) as minkindr forms it: (q^-1, -(q^-1).rotate(t)) — for the exact re-evaluation path
+    double* ef = &exact[8 * f];
+    ef[0] = qi.w; ef[1] = qi.x; ef[2] = qi.y; ef[3] = qi.z;
+    ef[4] = -ti.x; ef[5] = -ti.y; ef[6] = -ti.z; ef[7] = 0.0;
   }
 
   AMB_CUDA(ctx, ctx->frame_table.reserve(n * sizeof(uint8_t*)));
@@ -396,8 +483,10 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     for (size_t f = 0; f < n; ++f) table[f] = d_images[f];
     AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, table, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
   }
-  AMB_CUDA(ctx, ctx->frame_cull.reserve(12 * n * sizeof(double)));
+  AMB_CUDA(ctx, ctx->frame_cull.reserve(20 * n * sizeof(double)));   // [12 n cull | 8 n exact]
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.ptr, cull, 12 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_cull.as<double>() + 12 * n, exact, 8 * n * sizeof(double),
+                                cudaMemcpyHostToDevice, s));
 
   OrthoArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -511,6 +600,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.frame_base = static_cast<int>(f0);
     a.images = ctx->frame_table.as<const uint8_t*>() + f0;
     a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
+    a.exact_data = ctx->frame_cull.as<double>() + 12 * n + 8 * f0;
     const int grid = tiles_i * tiles_j;
     if (dominance) {
       if (select_only) {

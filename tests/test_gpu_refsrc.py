@@ -78,3 +78,37 @@ def test_ortho_from_pcl_equals_reference_cc():
     assert po.refsrc_ortho_from_pcl_process(po.make_geometry(rows, cols, res), o, xyz, inten, 2, False) == 0
     assert np.array_equal(gm["ortho"] == 255.0, o == 255.0)
     assert ulp_diff(gm["ortho"], o).max() <= 1
+
+
+def test_full_size_c3_stripe_equals_reference_sources():
+    """BASELINE config C3 at FULL size — 250 frames of 4000x3000 over 8000x8000 @ 0.5 m — on a 24-column stripe: the CUDA
+    path (stripe context, host frames) against the reference's own ortho-backward-grid.cc restricted to the same cells.
+    Every frame index and every pixel must be identical."""
+    rows = cols = 8000
+    res = 0.5
+    c0, c1 = 3988, 4012
+    camd = dict(synth.C3_CAMERA)
+    poses = synth.lawnmower_poses(10, 25, rows * res / 2, cols * res / 2, 600.0, seed=4)
+    imgs = [synth.procedural_image(k, camd["width"], camd["height"]) for k in range(len(poses))]
+    qx, qy = synth.grid_positions(rows, cols, res)
+    elev_stripe = np.asfortranarray(synth.terrain(qx[:, None], qy[None, c0:c1]).astype(np.float32))
+
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res),
+                           layer_names=("ortho", "elevation", "elevation_angle", "observation_index")).getMutable()
+    gm.layers["elevation"][:, c0:c1] = elev_stripe
+    gm.context(0, (c0, c1))
+    amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), gm).process(poses, imgs, gm)
+
+    L = {"elevation": np.full((rows, cols), np.nan, np.float32, order="F"),
+         "elevation_angle": np.zeros((rows, cols), np.float32, order="F"),
+         "observation_index": np.full((rows, cols), np.nan, np.float32, order="F"),
+         "ortho": np.full((rows, cols), 255.0, np.float32, order="F")}
+    L["elevation"][:, c0:c1] = elev_stripe
+    st, _ = po.refsrc_ortho_process(po.make_geometry(rows, cols, res), L, po.make_camera(**camd), poses, imgs,
+                                    cell_range=(rows * c0, rows * c1))
+    assert st == 0, po.refsrc_last_error()
+    a, b = gm["observation_index"][:, c0:c1], L["observation_index"][:, c0:c1]
+    assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+    assert np.array_equal(gm["ortho"][:, c0:c1].view(np.uint32), L["ortho"][:, c0:c1].view(np.uint32))
+    assert ulp_diff(gm["elevation_angle"][:, c0:c1], L["elevation_angle"][:, c0:c1]).max() <= 1
+    assert (~np.isnan(b)).all() and len(np.unique(b)) > 20      # every cell seen; many different winners along the stripe
