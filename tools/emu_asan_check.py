@@ -21,7 +21,8 @@ subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-f
                        "-fsanitize=address", "-fno-omit-frame-pointer", "-I" + os.path.join(build_emu.HERE, "include"), "-I" + B,
                        "-I" + build_emu.CSRC, "-I" + os.path.join(ROOT, "include")] +
                       sorted(os.path.join(B, f) for f in os.listdir(B) if f.endswith("_emu.cc")) +
-                      [os.path.join(build_emu.HERE, "emu_runtime.cc"), "-o", ASAN_LIB])
+                      sorted(os.path.join(build_emu.CSRC, f) for f in os.listdir(build_emu.CSRC) if f.endswith(".cc")) +
+                      [os.path.join(build_emu.HERE, "emu_runtime.cc"), "-ldl", "-o", ASAN_LIB])
 L = C.CDLL(ASAN_LIB)
 for name, (restype, argtypes) in _lib.SYMBOLS.items():
     fn = getattr(L, name); fn.restype = restype; fn.argtypes = argtypes
