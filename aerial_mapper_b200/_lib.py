@@ -25,7 +25,7 @@ LAYER_NAMES = ("ortho", "elevation", "elevation_angle", "num_observations", "ele
                "observation_index", "observation_index_first", "colored_ortho")
 LAYER_ID = {name: k for k, name in enumerate(LAYER_NAMES)}
 
-DIST_NONE, DIST_RADTAN, DIST_EQUIDISTANT = 0, 1, 2
+DIST_NONE, DIST_RADTAN, DIST_EQUIDISTANT, DIST_FOV = 0, 1, 2, 3
 DSM_F64, DSM_F32 = 0, 1
 
 

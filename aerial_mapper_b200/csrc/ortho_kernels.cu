@@ -146,6 +146,20 @@ __device__ __noinline__ bool exact_project(const OrthoArgs& a, double x, double 
       u = __dmul_rn(u, s);
       v = __dmul_rn(v, s);
     }
+  } else if (DIST == AMB_DIST_FOV) {
+    // oracle/thirdparty_math.h, FOV branch, operation by operation (tan(w/2) = a.d1, evaluated by the host libm)
+    const double r = sqrt(__dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v)));
+    const double at = atan(__dmul_rn(__dmul_rn(2.0, a.d1), r));
+    double s;
+    if (__dmul_rn(a.d0, a.d0) < 1e-5) {
+      s = 1.0;
+    } else if (__dmul_rn(r, r) < 1e-5) {
+      s = __ddiv_rn(__dmul_rn(2.0, a.d1), a.d0);
+    } else {
+      s = __ddiv_rn(at, __dmul_rn(r, a.d0));
+    }
+    u = __dmul_rn(u, s);
+    v = __dmul_rn(v, s);
   }
   *kx = __dadd_rn(__dmul_rn(a.fu, u), a.cu);
   *ky = __dadd_rn(__dmul_rn(a.fv, v), a.cv);
@@ -198,6 +212,14 @@ __device__ __forceinline__ bool project(const OrthoArgs& a, double x, double y, 
       u *= s;
       v *= s;
     }
+  } else if (DIST == AMB_DIST_FOV) {
+    // aslam FisheyeDistortion, d0 = w, d1 = tan(w/2) from the HOST libm (restated from recollection of upstream: see
+    // AMB_DIST_FOV in include/aerial_mapper_b200.h)
+    const double r = sqrt(u * u + v * v);
+    double s = 1.0;
+    if (!(a.d0 * a.d0 < 1e-5)) s = (r * r < 1e-5) ? 2.0 * a.d1 / a.d0 : atan(2.0 * a.d1 * r) / (r * a.d0);
+    u *= s;
+    v *= s;
   }
   *kx = a.fu * u + a.cu;
   *ky = a.fv * v + a.cv;
@@ -372,6 +394,18 @@ bool compute_view_cone(const amb_camera& cam, double* cos_c, double* sin_c, doub
     if (thc < 0.0) thc = step;
     if (thc >= half_pi - 1e-3) return false;
     rc = std::tan(thc);
+  } else if (cam.dist_type == AMB_DIST_FOV) {
+    // |D| = atan(2 tan(w/2) r) / w (or r itself for w^2 < 1e-5): increasing in r, bounded by (pi/2)/w.  A ray lands inside
+    // the raster only if |D| <= dmax, i.e. r <= tan(w dmax) / (2 tan(w/2)) — when w dmax reaches pi/2 every ray might.
+    const double w = k[0];
+    if (w * w < 1e-5) {
+      rc = dmax;
+    } else {
+      const double wd = std::fabs(w) * dmax;
+      if (!(wd < 1.5707963267948966 - 1e-3)) return false;
+      rc = std::tan(wd) / (2.0 * std::fabs(std::tan(w / 2.)));
+      if (!(rc > 0.0) || !std::isfinite(rc)) return false;
+    }
   } else {
     return false;
   }
@@ -420,7 +454,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   if (colored_ortho ? channels != 3 : channels != 1) return AMB_ERR_SIZE_MISMATCH;
   if (camera->width <= 0 || camera->height <= 0 || row_step < static_cast<size_t>(camera->width) * channels)
     return AMB_ERR_SIZE_MISMATCH;
-  if (camera->dist_type < AMB_DIST_NONE || camera->dist_type > AMB_DIST_EQUIDISTANT) return AMB_ERR_UNSUPPORTED;
+  if (camera->dist_type < AMB_DIST_NONE || camera->dist_type > AMB_DIST_FOV) return AMB_ERR_UNSUPPORTED;
   const int out_layer = colored_ortho ? AMB_LAYER_COLORED_ORTHO : AMB_LAYER_ORTHO;
   const int need[4] = {AMB_LAYER_ELEVATION, AMB_LAYER_ELEVATION_ANGLE, AMB_LAYER_OBSERVATION_INDEX, out_layer};
   for (int l : need) {
@@ -526,6 +560,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   a.res = g.resolution;
   a.fu = camera->fu; a.fv = camera->fv; a.cu = camera->cu; a.cv = camera->cv;
   a.d0 = camera->dist[0]; a.d1 = camera->dist[1]; a.d2 = camera->dist[2]; a.d3 = camera->dist[3];
+  if (camera->dist_type == AMB_DIST_FOV) a.d1 = std::tan(camera->dist[0] / 2.);  // FOV: the kernels take tan(w/2) from here
   a.do_cull = ctx->ortho_brute_force ? 0 : 1;
   double cc = 0.0, sc = 1.0, tc = 0.0;
   a.cone = compute_view_cone(*camera, &cc, &sc, &tc) ? 1 : 0;
@@ -563,6 +598,20 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
       if (r_th + lip * step >= r_in) break;
       th = b;
     }
+    if (th > 1e-3 && camera->fu > 0.0 && camera->fv > 0.0) {
+      a.dom_theta_in = th;
+      a.dom_margin = 1e-4;
+      dominance = true;
+    }
+  } else if (ctx->ortho_dominance && a.do_cull && a.cone && !a.rect && a.dist_type == AMB_DIST_FOV) {
+    // FOV: radius atan(2 tan(w/2) tan(theta)) / w, increasing — every ray with that radius below the distance to the
+    // nearest raster edge is imaged: tan(theta_in) = tan(w r_in) / (2 tan(w/2))
+    const double w = std::fabs(camera->dist[0]);
+    const double r_in = std::min(std::min(camera->cu, camera->width - camera->cu) / std::fabs(camera->fu),
+                                 std::min(camera->cv, camera->height - camera->cv) / std::fabs(camera->fv)) * (1.0 - 1e-9);
+    double tan_in = r_in;
+    if (w * w >= 1e-5) tan_in = (w * r_in < 1.5) ? std::tan(w * r_in) / (2.0 * std::fabs(std::tan(w / 2.))) : -1.0;
+    const double th = tan_in > 0.0 ? std::atan(tan_in) * (1.0 - 1e-9) : 0.0;
     if (th > 1e-3 && camera->fu > 0.0 && camera->fv > 0.0) {
       a.dom_theta_in = th;
       a.dom_margin = 1e-4;
@@ -608,6 +657,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
           ortho_kernel_dom<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
         } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
           ortho_kernel_dom<AMB_DIST_EQUIDISTANT, true><<<grid, kOrthoThreads, 0, s>>>(a);
+        } else if (a.dist_type == AMB_DIST_FOV) {
+          ortho_kernel_dom<AMB_DIST_FOV, true><<<grid, kOrthoThreads, 0, s>>>(a);
         } else {
           ortho_kernel_dom<AMB_DIST_NONE, true><<<grid, kOrthoThreads, 0, s>>>(a);
         }
@@ -615,6 +666,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
         ortho_kernel_dom<AMB_DIST_RADTAN, false><<<grid, kOrthoThreads, 0, s>>>(a);
       } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
         ortho_kernel_dom<AMB_DIST_EQUIDISTANT, false><<<grid, kOrthoThreads, 0, s>>>(a);
+      } else if (a.dist_type == AMB_DIST_FOV) {
+        ortho_kernel_dom<AMB_DIST_FOV, false><<<grid, kOrthoThreads, 0, s>>>(a);
       } else {
         ortho_kernel_dom<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
       }
@@ -623,6 +676,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
         ortho_kernel<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
       } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
         ortho_kernel<AMB_DIST_EQUIDISTANT, true><<<grid, kOrthoThreads, 0, s>>>(a);
+      } else if (a.dist_type == AMB_DIST_FOV) {
+        ortho_kernel<AMB_DIST_FOV, true><<<grid, kOrthoThreads, 0, s>>>(a);
       } else {
         ortho_kernel<AMB_DIST_NONE, true><<<grid, kOrthoThreads, 0, s>>>(a);
       }
@@ -630,6 +685,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
       ortho_kernel<AMB_DIST_RADTAN, false><<<grid, kOrthoThreads, 0, s>>>(a);
     } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
       ortho_kernel<AMB_DIST_EQUIDISTANT, false><<<grid, kOrthoThreads, 0, s>>>(a);
+    } else if (a.dist_type == AMB_DIST_FOV) {
+      ortho_kernel<AMB_DIST_FOV, false><<<grid, kOrthoThreads, 0, s>>>(a);
     } else {
       ortho_kernel<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
     }

@@ -106,7 +106,9 @@ def _quat_from_matrix(R):
 
 
 _DISTORTION = {"none": _lib.DIST_NONE, "null": _lib.DIST_NONE, "radial-tangential": _lib.DIST_RADTAN,
-               "radtan": _lib.DIST_RADTAN, "equidistant": _lib.DIST_EQUIDISTANT}
+               "radtan": _lib.DIST_RADTAN, "equidistant": _lib.DIST_EQUIDISTANT,
+               "fisheye": _lib.DIST_FOV, "fov": _lib.DIST_FOV}  # aslam FisheyeDistortion (restated from recollection, see
+                                                                  # include/aerial_mapper_b200.h AMB_DIST_FOV)
 
 
 def load_camera_rig_from_file(filename_ncameras_yaml, camera_index=0):

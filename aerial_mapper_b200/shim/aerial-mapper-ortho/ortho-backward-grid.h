@@ -49,6 +49,7 @@ class OrthoBackwardGrid {
       case aslam::Distortion::Type::kNoDistortion: cam.dist_type = AMB_DIST_NONE; break;
       case aslam::Distortion::Type::kRadTan: cam.dist_type = AMB_DIST_RADTAN; break;
       case aslam::Distortion::Type::kEquidistant: cam.dist_type = AMB_DIST_EQUIDISTANT; break;
+      case aslam::Distortion::Type::kFisheye: cam.dist_type = AMB_DIST_FOV; break;
       default: LOG(FATAL) << "aerial_mapper_b200: unsupported distortion model"; cam.dist_type = AMB_DIST_NONE;
     }
     if (cam.dist_type != AMB_DIST_NONE)

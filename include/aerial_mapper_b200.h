@@ -75,7 +75,13 @@ typedef enum amb_layer_id {
 typedef enum amb_distortion {
   AMB_DIST_NONE = 0,
   AMB_DIST_RADTAN = 1,       /* k1 k2 p1 p2 */
-  AMB_DIST_EQUIDISTANT = 2   /* k1 k2 k3 k4 */
+  AMB_DIST_EQUIDISTANT = 2,  /* k1 k2 k3 k4 */
+  /* aslam FisheyeDistortion ("FOV" model), dist[0] = w.  PROVENANCE: unlike rad-tan / equidistant (cross-checked against
+   * OpenCV), this branch is restated from RECOLLECTION of upstream aslam_cv2 distortion-fisheye.cc — the source is not
+   * under the reference tree and no offline cross-check exists.  Formula as implemented: r_d/r_u = atan(2 tan(w/2) r_u) /
+   * (r_u w); w*w < 1e-5 -> 1; r_u*r_u < 1e-5 -> 2 tan(w/2) / w.  The two 1e-5 thresholds and the limit value are the
+   * parts to verify against the upstream file before relying on bit-level parity for this model. */
+  AMB_DIST_FOV = 3
 } amb_distortion;
 
 typedef struct amb_camera {

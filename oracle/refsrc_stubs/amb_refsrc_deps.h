@@ -376,6 +376,7 @@ class Camera {
     intrinsics_(3) = c.cv;
     const Distortion::Type t = c.dist_type == AMB_DIST_RADTAN        ? Distortion::Type::kRadTan
                                : c.dist_type == AMB_DIST_EQUIDISTANT ? Distortion::Type::kEquidistant
+                               : c.dist_type == AMB_DIST_FOV         ? Distortion::Type::kFisheye
                                                                      : Distortion::Type::kNoDistortion;
     distortion_ = Distortion(t, distortion_params_);
   }
@@ -391,6 +392,7 @@ class Camera {
     c_.cv = intrinsics(3);
     c_.dist_type = distortion.getType() == Distortion::Type::kRadTan        ? AMB_DIST_RADTAN
                    : distortion.getType() == Distortion::Type::kEquidistant ? AMB_DIST_EQUIDISTANT
+                   : distortion.getType() == Distortion::Type::kFisheye     ? AMB_DIST_FOV
                                                                             : AMB_DIST_NONE;
     for (int k = 0; k < 4; ++k) c_.dist[k] = distortion.getParameters()(k);
     c_.q_C_B[0] = 1.0;

@@ -13,6 +13,9 @@
  *   grid_map   colorVectorToValue(Vector3f)
  * Cross-checked in tests/test_oracle_ortho.py against cv2.projectPoints, cv2.fisheye.projectPoints and
  * scipy.spatial.transform.Rotation.  Build with -ffp-contract=off.
+ * NOT cross-checked: the FOV ("fisheye") distortion branch below.  OpenCV has no such model and the aslam_cv2 source is not
+ * available here; it is written from recollection of upstream distortion-fisheye.cc (thresholds 1e-5, limit 2 tan(w/2)/w).
+ * A GPU-vs-oracle match on that branch shows the CUDA path equals THIS restatement, nothing more.
  */
 #ifndef AMB_ORACLE_THIRDPARTY_MATH_H_
 #define AMB_ORACLE_THIRDPARTY_MATH_H_
@@ -159,6 +162,22 @@ inline ProjectionStatus project3(const amb_camera& cam, const Vec3& p, double* k
       x *= scaling;
       y *= scaling;
     }
+  } else if (cam.dist_type == AMB_DIST_FOV) {
+    /* aslam::FisheyeDistortion::distortUsingExternalCoefficients — FROM RECOLLECTION, unverified (see header) */
+    const double w = cam.dist[0];
+    const double r_u = std::sqrt(x * x + y * y);
+    const double tanwhalf = std::tan(w / 2.);
+    const double atan_wrd = std::atan(2. * tanwhalf * r_u);
+    double r_rd;
+    if (w * w < 1e-5) {
+      r_rd = 1.0;
+    } else if (r_u * r_u < 1e-5) {
+      r_rd = 2. * tanwhalf / w;
+    } else {
+      r_rd = atan_wrd / (r_u * w);
+    }
+    x *= r_rd;
+    y *= r_rd;
   }
   *kx = cam.fu * x + cam.cu;
   *ky = cam.fv * y + cam.cv;

@@ -18,11 +18,13 @@ from oracle import pyoracle as po
 pytestmark = pytest.mark.gpu
 
 EQUI = (0.01, -0.002, 0.0005, -0.0001)
+FOV = (0.9, 0.0, 0.0, 0.0)   # aslam FisheyeDistortion, w = 0.9 rad (AMB_DIST_FOV: restated from recollection of upstream —
+                             # these tests pin the CUDA path to the oracle's restatement, not to aslam_cv2 itself)
 
 
 def make_inputs(rows, cols, res, lines, per_line, agl, scale, colored, dist_type=1, dist=None, seed=4, **cam_kw):
     if dist is None:
-        dist = {0: (0, 0, 0, 0), 1: (-0.05, 0.01, 1e-4, 1e-4), 2: EQUI}[dist_type]
+        dist = {0: (0, 0, 0, 0), 1: (-0.05, 0.01, 1e-4, 1e-4), 2: EQUI, 3: FOV}[dist_type]
     camd = synth.scaled_camera(scale, dist_type=dist_type, dist=dist)
     camd.update(cam_kw)
     poses = synth.lawnmower_poses(lines, per_line, rows * res / 2, cols * res / 2, agl, seed, jitter_pos=agl / 100)
@@ -65,7 +67,7 @@ def assert_parity(gm, L, colored, cols=slice(None)):
 
 
 @pytest.mark.parametrize("colored", [False, True])
-@pytest.mark.parametrize("dist_type", [0, 1, 2])
+@pytest.mark.parametrize("dist_type", [0, 1, 2, 3])
 def test_matches_oracle(colored, dist_type):
     rows, cols, res = 200, 160, 0.5
     camd, poses, imgs = make_inputs(rows, cols, res, 3, 4, 60.0, 0.1, colored, dist_type)
@@ -311,3 +313,42 @@ def test_host_mirrors_stream_results_back_with_the_same_bits():
         gm.sync()
         for k in names:
             assert np.array_equal(gm[k].view(np.uint32), ref[k].view(np.uint32)), k
+
+
+# ---- FOV ("fisheye") distortion, AMB_DIST_FOV -------------------------------------------------------------------------
+# What these tests do and do not show: the aslam_cv2 source is not available offline and OpenCV has no FOV model, so the
+# oracle's branch (oracle/thirdparty_math.h) is written from recollection of upstream distortion-fisheye.cc.  The tests pin
+# the CUDA path — fast path, exact re-evaluation, cull cones — to THAT restatement bit for bit; they cannot confirm the
+# restatement's constants (the two 1e-5 thresholds, the small-radius limit) against aslam_cv2.
+def test_fov_with_negligible_w_is_the_undistorted_pinhole():
+    # w*w < 1e-5: the model's first limit branch multiplies by 1 — every output bit equals dist_type 0
+    rows, cols, res = 160, 128, 0.5
+    camd0, poses, imgs = make_inputs(rows, cols, res, 3, 4, 60.0, 0.1, False, 0)
+    camd3 = dict(camd0, dist_type=3, dist=(1e-3, 0.0, 0.0, 0.0))
+    elev = synth.analytic_elevation(rows, cols, res)
+    a = gpu_ortho(rows, cols, res, elev, camd0, poses, imgs, False)
+    b = gpu_ortho(rows, cols, res, elev, camd3, poses, imgs, False)
+    for k in ("ortho", "elevation_angle", "observation_index"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert_parity(b, oracle_ortho(rows, cols, res, elev, camd3, poses, imgs, False), False)
+
+
+def test_fov_small_radius_branch_and_cull_variants():
+    # a camera exactly above a cell centre (r_u*r_u < 1e-5 for the cells around the nadir point: the second limit branch),
+    # wide w; brute force, plain cull and dominance cull must all give the oracle's layers
+    rows, cols, res = 192, 160, 0.25
+    camd, poses, imgs = make_inputs(rows, cols, res, 2, 3, 40.0, 0.08, False, 3, dist=(1.2, 0, 0, 0))
+    qx, qy = synth.grid_positions(rows, cols, res)
+    poses[0][:2] = (qx[90], qy[70])
+    poses[0][3:] = (0.0, 1.0, 0.0, 0.0)      # exact nadir: the cell below projects to r_u = 0
+    elev = synth.analytic_elevation(rows, cols, res)
+    L = oracle_ortho(rows, cols, res, elev, camd, poses, imgs, False)
+    os.environ["AMB_ORTHO_DOMINANCE"] = "1"
+    try:
+        assert_parity(gpu_ortho(rows, cols, res, elev, camd, poses, imgs, False), L, False)
+        assert_parity(gpu_ortho(rows, cols, res, elev, camd, poses, imgs, False, brute=True), L, False)
+        os.environ["AMB_ORTHO_DOMINANCE"] = "0"
+        assert_parity(gpu_ortho(rows, cols, res, elev, camd, poses, imgs, False), L, False)
+    finally:
+        os.environ.pop("AMB_ORTHO_DOMINANCE", None)
+    assert (~np.isnan(L["observation_index"])).mean() > 0.5

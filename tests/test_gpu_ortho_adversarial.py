@@ -105,14 +105,14 @@ def test_exact_angle_tie_follows_the_float32_rounded_running_best():
     assert np.array_equal(col, col2)          # mirrored frames: the same pattern whichever comes first
 
 
-@pytest.mark.parametrize("dist_type", [0, 1, 2])
+@pytest.mark.parametrize("dist_type", [0, 1, 2, 3])
 def test_poses_perturbed_across_the_boundaries(dist_type):
     """Keypoints within ~1e-13..1e-6 px of raster edges and half-integers, camera planes within 1e-12 m of the minimum
     depth, near-ties of the observation angle: whatever the oracle decides, the CUDA path decides."""
     rng = np.random.default_rng(100 + dist_type)
     rows, cols, res = 40, 36, 0.5
     qx, qy = synth.grid_positions(rows, cols, res)
-    dist = {0: (0, 0, 0, 0), 1: (-0.05, 0.01, 1e-4, 1e-4), 2: (0.01, -0.002, 0.0005, -0.0001)}[dist_type]
+    dist = {0: (0, 0, 0, 0), 1: (-0.05, 0.01, 1e-4, 1e-4), 2: (0.01, -0.002, 0.0005, -0.0001), 3: (0.9, 0, 0, 0)}[dist_type]
     for trial in range(24):
         camd = camera(40, 36, 20.0, 18.0)
         camd.update(dist_type=dist_type, dist=dist)

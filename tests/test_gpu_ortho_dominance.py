@@ -31,7 +31,7 @@ def both(monkeypatch, *args, **kw):
 
 
 @pytest.mark.parametrize("colored", [False, True])
-@pytest.mark.parametrize("dist_type", [0, 1, 2])      # 2 (equidistant): inner view CONE instead of the inner rectangle
+@pytest.mark.parametrize("dist_type", [0, 1, 2, 3])   # 2 (equidistant), 3 (FOV): inner view CONE instead of the inner rectangle
 def test_dominance_cull_changes_nothing(monkeypatch, colored, dist_type):
     rows, cols, res = 200, 160, 0.5
     camd, poses, imgs = make_inputs(rows, cols, res, 3, 4, 60.0, 0.1, colored, dist_type)

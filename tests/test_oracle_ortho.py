@@ -177,3 +177,25 @@ def test_argument_checks():
     g, cam = po.make_geometry(4, 4, 1.0), po.make_camera(8, 8, 4, 4, 4, 4)
     L = fresh_layers(4, 4, np.zeros((4, 4), np.float32))
     assert po.ortho_process(g, L, cam, np.zeros((0, 7)), [])[0] == -1  # CHECK(!T_G_Bs.empty())
+
+
+def test_fov_branch_is_the_stated_formula():
+    """The oracle's FOV branch against the SAME stated formula evaluated with numpy: r_d = atan(2 tan(w/2) r) / w, limits
+    w*w < 1e-5 -> r and r*r < 1e-5 -> 2 tan(w/2) r / w.  This checks the C++ transcription only.  It is NOT an independent
+    cross-check of the model (unlike rad-tan / equidistant vs OpenCV above): the formula itself is recalled from upstream
+    aslam_cv2 distortion-fisheye.cc, which is not available offline."""
+    rng = np.random.default_rng(8)
+    for w in (0.9, 1.2, 0.3, 1e-3):
+        cam = po.make_camera(width=4000, height=3000, fu=1500.0, fv=1490.0, cu=2000.0, cv=1500.0, dist_type=3,
+                             dist=(w, 0.0, 0.0, 0.0))
+        for _ in range(200):
+            p = np.array([rng.normal(0, 2.0), rng.normal(0, 2.0), rng.uniform(0.5, 8.0)])
+            if rng.random() < 0.1:
+                p[:2] *= 1e-4          # small-radius limit branch
+            u, v = p[0] / p[2], p[1] / p[2]
+            r = np.hypot(u, v)
+            t = np.tan(w / 2.0)
+            s = 1.0 if w * w < 1e-5 else (2 * t / w if r * r < 1e-5 else np.arctan(2 * t * r) / (r * w))
+            want = np.array([1500.0 * u * s + 2000.0, 1490.0 * v * s + 1500.0])
+            got = po.project3(cam, p)[1]
+            assert np.allclose(got, want, rtol=1e-13, atol=1e-10), (w, p, got, want)
