@@ -112,6 +112,18 @@ SYMBOLS = {
                                            C.c_int32]),
     "amb_ortho_set_brute_force": (C.c_int, [_P, C.c_int]),
     "amb_ortho_set_dominance_cull": (C.c_int, [_P, C.c_int]),
+    "amb_multi_create": (C.c_int, [C.POINTER(Geometry), C.c_int, C.POINTER(_P)]),
+    "amb_multi_destroy": (None, [_P]),
+    "amb_multi_size": (C.c_int, [_P]),
+    "amb_multi_context": (_P, [_P, C.c_int]),
+    "amb_multi_last_error": (C.c_char_p, [_P]),
+    "amb_multi_init_layers": (C.c_int, [_P]),
+    "amb_multi_upload_layer": (C.c_int, [_P, C.c_int, _P]),
+    "amb_multi_download_layer": (C.c_int, [_P, C.c_int, _P]),
+    "amb_multi_set_host_mirror": (C.c_int, [_P, C.c_int, _P]),
+    "amb_multi_sync": (C.c_int, [_P]),
+    "amb_multi_dsm_process": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double]),
+    "amb_multi_ortho_process": (C.c_int, [_P, C.POINTER(Camera), _P, _P, C.c_size_t, C.c_int32, C.c_size_t, C.c_int32]),
     "amb_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "amb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "amb_host_free": (C.c_int, [_P]),

@@ -35,12 +35,11 @@ class Dsm {
     }
     CHECK(map);  // dsm.cc:194
     static_assert(sizeof(Eigen::Vector3d) == 3 * sizeof(double), "AoS double[3] expected");
-    amb_ctx* ctx = context_.get(*map);
+    context_.get(*map);
     context_.upload(map, "elevation", AMB_LAYER_ELEVATION);  // cells without neighbours keep their value
     const double* xyz = &point_cloud[0](0);
-    amb_shim::checkStatus(amb_dsm_process(ctx, xyz, point_cloud.size(), settings_.interpolation_radius,
-                                          settings_.center_easting, settings_.center_northing),
-                          ctx, "amb_dsm_process");
+    context_.dsmProcess(xyz, point_cloud.size(), settings_.interpolation_radius, settings_.center_easting,
+                        settings_.center_northing);
     context_.download(map, "elevation", AMB_LAYER_ELEVATION);
   }
 

@@ -336,6 +336,29 @@ int amb_ortho_set_brute_force(amb_ctx* ctx, int brute_force);
  * bits, ~1.2 instead of ~8.5 frames per cell at the benchmark geometry (tools/ortho_dominance_study.py). */
 int amb_ortho_set_dominance_cull(amb_ctx* ctx, int enable);
 
+/* ---- several GPUs of one process (amb_create(geom, n_gpus)) ----
+ * amb_multi owns one context per device 0..n_gpus-1, each with a contiguous column stripe (width ceil(cols / n_gpus)).
+ * Entry points mirror the single-context ones with FULL host layers / the whole host cloud / all host frames, as the
+ * reference's classes receive them (dsm.cc:186-201, ortho-backward-grid.cc:223-239); the stripes run concurrently.
+ * DSM: every device gets the whole cloud over its own PCIe link and bins what reaches its stripe — nothing arrives sharded,
+ * so this path has no exchange step (a cloud that arrives sharded uses amb_dsm_process_sharded* per context).  Every
+ * stripe is bit-identical to the same columns of a single-GPU run. */
+typedef struct amb_multi amb_multi;
+int amb_multi_create(const amb_geometry* geom, int n_gpus, amb_multi** out);
+void amb_multi_destroy(amb_multi* m);
+int amb_multi_size(const amb_multi* m);                 /* stripes actually created (<= n_gpus) */
+amb_ctx* amb_multi_context(amb_multi* m, int rank);     /* the stripe's context, for the per-context settings */
+const char* amb_multi_last_error(const amb_multi* m);
+int amb_multi_init_layers(amb_multi* m);
+int amb_multi_upload_layer(amb_multi* m, int layer, const float* host_full);   /* rows x cols floats, column-major */
+int amb_multi_download_layer(amb_multi* m, int layer, float* host_full);
+int amb_multi_set_host_mirror(amb_multi* m, int layer, float* host_full);      /* page-locked; NULL clears */
+int amb_multi_sync(amb_multi* m);
+int amb_multi_dsm_process(amb_multi* m, const double* xyz, size_t n, int32_t interpolation_radius,
+                          double center_easting, double center_northing);
+int amb_multi_ortho_process(amb_multi* m, const amb_camera* camera, const double* T_G_B, const uint8_t* const* images,
+                            size_t n, int32_t channels, size_t row_step, int32_t colored_ortho);
+
 /* ---- measurement ---- */
 int amb_get_timings(amb_ctx* ctx, amb_timings* out);
 

@@ -133,3 +133,25 @@ def test_demo_sequence_through_the_cpp_shim(tmp_path, colored):
     for k, name in enumerate(["elevation", "elevation_angle", "observation_index", "ortho", "colored_ortho"]):
         assert np.array_equal(got[k].view(np.uint32), gm[name].view(np.uint32)), name
     assert np.isnan(got[0]).any() and (~np.isnan(got[2])).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("colored", [False, True])
+def test_demo_through_the_shim_on_several_gpus_of_one_process(tmp_path, colored, gpu_count):
+    """AMB_SHIM_GPUS=N: the drop-in classes spread the map's column stripes over N GPUs of the demo process (amb_multi_*:
+    one context per device, the whole cloud to every device, all frames per stripe) — every layer bit-identical to the
+    single-GPU run of the same binary.  Needs >= 2 devices (e.g. `gpurun --gpus 2`)."""
+    if gpu_count < 2:
+        pytest.skip("needs at least two CUDA devices")
+    exe = build_demo(tmp_path)
+    scen, (rows, cols, res, xyz, camd, poses, imgs) = make_scenario(tmp_path, colored, rows=200, cols=160)
+    outs = []
+    for gpus in (1, min(gpu_count, 4)):
+        out = tmp_path / ("layers_%d.bin" % gpus)
+        env = dict(os.environ, AMB_SHIM_GPUS=str(gpus))
+        r = subprocess.run([exe, str(scen), str(out)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs.append(read_layers(out, rows, cols))
+    for k, name in enumerate(LAYERS):
+        assert np.array_equal(outs[0][k].view(np.uint32), outs[1][k].view(np.uint32)), name
+    assert np.isnan(outs[0][0]).any() and (~np.isnan(outs[0][2])).any()
