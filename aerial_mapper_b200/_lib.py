@@ -9,6 +9,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaerial_mapper_b200.so")
+if os.environ.get("AMB_LIB_PATH"):   # development only: an alternative build of the SAME library (kernel tuning variants)
+    LIB_PATH = os.environ["AMB_LIB_PATH"]
 CSRC = os.path.join(_HERE, "csrc")
 
 AMB_OK = 0

@@ -225,8 +225,10 @@ void amb_destroy(amb_ctx* ctx) {
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layer_copy_event[l]) cudaEventDestroy(ctx->layer_copy_event[l]);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-  ctx->stage.release();
-  if (ctx->stage_event) cudaEventDestroy(ctx->stage_event);
+  for (int k = 0; k < 2; ++k) {
+    ctx->stages[k].release();
+    if (ctx->stage_events[k]) cudaEventDestroy(ctx->stage_events[k]);
+  }
   if (ctx->host_flags) cudaFreeHost(ctx->host_flags);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

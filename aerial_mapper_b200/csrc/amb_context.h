@@ -143,8 +143,12 @@ struct amb_ctx {
   cudaStream_t copy_stream = nullptr;  // H2D staging overlapped with compute
   cudaEvent_t events[amb::EV_COUNT] = {};
   cudaEvent_t copy_done[2] = {};
-  amb::HostStage stage;                 // pinned staging of per-call tables
-  cudaEvent_t stage_event = nullptr;    // last use of `stage` by an asynchronous copy
+  // pinned staging of per-call tables, double-buffered: call k fills stages[k & 1] while the asynchronous copies and the
+  // kernel of call k - 1 may still read stages[(k - 1) & 1] — with one buffer the host could not prepare the next
+  // process() before the previous kernel had finished (measured: ortho-only steps were host-bound)
+  amb::HostStage stages[2];
+  cudaEvent_t stage_events[2] = {nullptr, nullptr};   // last use of each buffer by an asynchronous copy
+  unsigned int stage_turn = 0;
   unsigned int* host_flags = nullptr;   // pinned: device flags read back at the end of a host entry point
   float* host_mirror[AMB_NUM_LAYERS] = {};  // pinned host slabs that receive a layer as soon as it is final
   amb::CompactMirror compact[AMB_NUM_LAYERS];  // opt-in one-byte transport (amb_set_host_mirror_compact)

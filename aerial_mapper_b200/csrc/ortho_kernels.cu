@@ -23,9 +23,20 @@ namespace amb {
 namespace {
 
 constexpr int kMaxFramesPerLaunch = 512;
-constexpr int OTI = 32;  // tile extent along i (rows; contiguous in memory)
+#ifndef AMB_OTI
+#define AMB_OTI 32
+#endif
+constexpr int OTI = AMB_OTI;  // tile extent along i (rows; contiguous in memory): a multiple of 32
+static_assert(OTI % 32 == 0, "a warp covers 32 consecutive rows");
 constexpr int OTJ = 32;  // tile extent along j
-constexpr int kOStrip = 4;  // cells per thread (adjacent along j)
+#ifndef AMB_OSTRIP
+#define AMB_OSTRIP 4
+#endif
+#ifndef AMB_OBPS
+#define AMB_OBPS 4   // measured at joint_10k: 3 blocks/SM (80 registers) 3.04 ms, 4 blocks/SM (64 registers) 2.86 ms
+#endif
+constexpr int kOStrip = AMB_OSTRIP;  // cells per thread (adjacent along j); tuning knobs AMB_OSTRIP / AMB_OBPS (resident blocks
+                                     // per SM the register allocation targets) are compile-time: see DESIGN.md §4.2
 constexpr int kOrthoThreads = OTI * OTJ / kOStrip;
 
 struct FrameConst {
@@ -473,14 +484,17 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   const V3 r_tmp = qrot(q_B_C, t_C_B);
   const V3 t_B_C = {-r_tmp.x, -r_tmp.y, -r_tmp.z};
   // per-call tables live in pinned staging (see HostStage); the previous call's copies must have left it
-  if (!ctx->stage_event) AMB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_event, cudaEventDisableTiming));
-  AMB_CUDA(ctx, cudaEventSynchronize(ctx->stage_event));
-  AMB_CUDA(ctx, ctx->stage.reserve(n * (sizeof(FrameConst) + 20 * sizeof(double) + 8 * sizeof(int) +
+  const int turn = static_cast<int>(ctx->stage_turn++ & 1u);
+  HostStage& stage = ctx->stages[turn];
+  cudaEvent_t& stage_event = ctx->stage_events[turn];
+  if (!stage_event) AMB_CUDA(ctx, cudaEventCreateWithFlags(&stage_event, cudaEventDisableTiming));
+  AMB_CUDA(ctx, cudaEventSynchronize(stage_event));   // the call before the previous one: long finished in practice
+  AMB_CUDA(ctx, stage.reserve(n * (sizeof(FrameConst) + 20 * sizeof(double) + 8 * sizeof(int) +
                                         sizeof(FrameRect) + sizeof(uint8_t*)) + 1024));
-  ctx->stage.used = 0;
-  FrameConst* fcs = ctx->stage.take<FrameConst>(n);
-  double* cull = ctx->stage.take<double>(12 * n);
-  double* exact = ctx->stage.take<double>(8 * n);
+  stage.used = 0;
+  FrameConst* fcs = stage.take<FrameConst>(n);
+  double* cull = stage.take<double>(12 * n);
+  double* exact = stage.take<double>(8 * n);
   for (size_t f = 0; f < n; ++f) {
     const double* p = T_G_B + 7 * f;
     const Quat q_G_B = {p[3], p[4], p[5], p[6]};
@@ -513,7 +527,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   }
   unsigned int* counters = ctx->counters.as<unsigned int>();
   if (!select_only) {
-    const uint8_t** table = ctx->stage.take<const uint8_t*>(n);
+    const uint8_t** table = stage.take<const uint8_t*>(n);
     for (size_t f = 0; f < n; ++f) table[f] = d_images[f];
     AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_table.ptr, table, n * sizeof(uint8_t*), cudaMemcpyHostToDevice, s));
   }
@@ -536,8 +550,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     AMB_CUDA(ctx, ctx->ortho_pix.reserve(cells * sizeof(unsigned int)));
     AMB_CUDA(ctx, ctx->ortho_bbox.reserve(n * 4 * sizeof(int)));
     AMB_CUDA(ctx, cudaMemsetAsync(ctx->ortho_pix.ptr, 0xff, cells * sizeof(unsigned int), s));
-    bbox = ctx->stage.take<int>(4 * n);
-    bbox_back = ctx->stage.take<int>(4 * n);
+    bbox = stage.take<int>(4 * n);
+    bbox_back = stage.take<int>(4 * n);
     for (size_t f = 0; f < n; ++f) {
       bbox[4 * f + 0] = bbox[4 * f + 1] = 0x7fffffff;
       bbox[4 * f + 2] = bbox[4 * f + 3] = -1;
@@ -700,7 +714,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   if (mst == AMB_OK) mst = mirror_layer(ctx, AMB_LAYER_OBSERVATION_INDEX);
   if (mst != AMB_OK) return mst;
   if (!select_only) {
-    AMB_CUDA(ctx, cudaEventRecord(ctx->stage_event, s));
+    AMB_CUDA(ctx, cudaEventRecord(stage_event, s));
     return mirror_layer(ctx, out_layer);
   }
 
@@ -713,7 +727,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   }
   AMB_CUDA(ctx, cudaStreamSynchronize(s));
   bbox = bbox_back;
-  FrameRect* rects = ctx->stage.take<FrameRect>(n);
+  FrameRect* rects = stage.take<FrameRect>(n);
   size_t total = 0;
   for (size_t f = 0; f < n; ++f) {
     FrameRect& r = rects[f];
@@ -749,7 +763,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
                                                     a.out_layer, cells, channels, a.colored);
   ctx->ortho_launches += 1;
   AMB_CUDA(ctx, cudaGetLastError());
-  AMB_CUDA(ctx, cudaEventRecord(ctx->stage_event, s));
+  AMB_CUDA(ctx, cudaEventRecord(stage_event, s));
   return mirror_layer(ctx, out_layer);
 }
 
