@@ -213,7 +213,7 @@ void amb_destroy(amb_ctx* ctx) {
   release_compact_mirrors(ctx);
   for (int l = 0; l < AMB_NUM_LAYERS; ++l)
     if (ctx->layers[l]) cudaFree(ctx->layers[l]);
-  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->point_ids, &ctx->intensities, &ctx->records, &ctx->point_order,
+  DeviceBuffer* bufs[] = {&ctx->points,  &ctx->point_ids, &ctx->intensities, &ctx->records, &ctx->records_tmp, &ctx->tile_offsets, &ctx->point_order, &ctx->bucket_flags,
                             &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
                           &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
                           &ctx->frame_cull, &ctx->frame_rects, &ctx->ortho_pix, &ctx->ortho_bbox};

@@ -165,7 +165,11 @@ struct amb_ctx {
   amb::DeviceBuffer point_ids;    // device copy of the caller's global point ids (sharded host entry point)
   amb::DeviceBuffer intensities;  // device copy of the caller's intensities (OrthoFromPcl host entry point)
   amb::DeviceBuffer records;      // bucket-sorted 32-byte point records
+  amb::DeviceBuffer records_tmp;  // two-level binning: the points as 32-byte records, tile by tile, grouped by coarse destination
+  amb::DeviceBuffer tile_offsets; // ... and the uint16 run starts, [(S + 1)][n_tiles]
+  std::vector<unsigned char> last_part_plan;
   amb::DeviceBuffer point_order;  // uint32 per record: canonical (original-index) visiting order inside a bucket
+  amb::DeviceBuffer bucket_flags; // one byte per bucket: the warp-per-cell kernel will read it (dsm_mark_buckets_kernel)
   amb::DeviceBuffer bin_starts;   // uint32 G[nb + 2]
   amb::DeviceBuffer block_sums;   // scan spine
   amb::DeviceBuffer empty_cells;  // uint32 list of cells that need the expanding-radius pass

@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restri
   }
 }
 
+#include "dsm_partition.inc"
+
 // K3b: canonical order inside every bucket (ascending original index = what a stable sort would give), as an
 // index array: order[s + r] = position of the bucket's r-th smallest original index.  Only the warp-per-cell
 // kernel needs it (the tile kernel orders every cell's points in shared memory); writing 4 bytes per point
@@ -333,33 +335,70 @@ __device__ __forceinline__ void rank_bucket(const PointRec* __restrict__ rec, un
   }
 }
 
+// `flags` (one byte per bucket, or nullptr = every bucket): only the buckets the warp-per-cell kernel is going to read
+// are ordered — dsm_mark_buckets_kernel sets the bytes from the cell list after the gather, this kernel clears them.
+// At the benchmark density ~30 % of the buckets are touched by a listed cell.
 __global__ void __launch_bounds__(256) dsm_bucket_order_kernel(const unsigned int* __restrict__ G,
                                                                unsigned int n_buckets,
                                                                const PointRec* __restrict__ rec,
-                                                               unsigned int* __restrict__ order) {
+                                                               unsigned int* __restrict__ order,
+                                                               unsigned char* __restrict__ flags) {
   constexpr int kMaxK = 32 * kSortRegs;  // bucket sizes handled through shared memory
   __shared__ __align__(16) unsigned int skeys[8][kMaxK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (unsigned int b = blockIdx.x * (blockDim.x >> 5) + warp; b < n_buckets; b += warps_total) {
-    const unsigned int s = G[b], e = G[b + 1];
-    const unsigned int k = e - s;
-    if (k == 0) continue;
-    if (k <= 32u) {
-      rank_bucket<1>(rec, order, skeys[warp], s, k, lane);
-    } else if (k <= 64u) {
-      rank_bucket<2>(rec, order, skeys[warp], s, k, lane);
-    } else if (k <= static_cast<unsigned int>(kMaxK)) {
-      rank_bucket<kSortRegs>(rec, order, skeys[warp], s, k, lane);
-    } else {
-      // far denser than the bucket size was chosen for: rank against the keys in global memory
-      for (unsigned int q = lane; q < k; q += 32) {
-        const unsigned int mine = rec_id(__ldg(&rec[s + q].idx));
-        unsigned int rank = 0;
-        for (unsigned int o = 0; o < k; ++o) rank += rec_id(__ldg(&rec[s + o].idx)) < mine ? 1u : 0u;
-        order[s + rank] = s + q;
-      }
+  // a warp takes 32 consecutive buckets at a time: one flag byte per lane, then the flagged ones in turn
+  for (unsigned int b0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32u; b0 < n_buckets; b0 += warps_total * 32u) {
+    const unsigned int bl = b0 + lane;
+    bool mine = bl < n_buckets;
+    if (mine && flags) {
+      mine = flags[bl] != 0;
+      if (mine) flags[bl] = 0;
     }
+    unsigned int todo = __ballot_sync(0xffffffffu, mine);
+    while (todo) {
+      const unsigned int b = b0 + static_cast<unsigned int>(__ffs(todo) - 1);
+      todo &= todo - 1u;
+      const unsigned int s = G[b], e = G[b + 1];
+      const unsigned int k = e - s;
+      if (k == 0) continue;
+      if (k <= 32u) {
+        rank_bucket<1>(rec, order, skeys[warp], s, k, lane);
+      } else if (k <= 64u) {
+        rank_bucket<2>(rec, order, skeys[warp], s, k, lane);
+      } else if (k <= static_cast<unsigned int>(kMaxK)) {
+        rank_bucket<kSortRegs>(rec, order, skeys[warp], s, k, lane);
+      } else {
+        // far denser than the bucket size was chosen for: rank against the keys in global memory
+        for (unsigned int q = lane; q < k; q += 32) {
+          const unsigned int mine_id = rec_id(__ldg(&rec[s + q].idx));
+          unsigned int rank = 0;
+          for (unsigned int o = 0; o < k; ++o) rank += rec_id(__ldg(&rec[s + o].idx)) < mine_id ? 1u : 0u;
+          order[s + rank] = s + q;
+        }
+      }
+      __syncwarp();  // skeys is reused by the next bucket
+    }
+  }
+}
+
+// The buckets the warp-per-cell kernel visits for the listed cells (window of the largest threshold, exactly the
+// bucket range dsm_cell_kernel derives): one thread per listed cell.
+__global__ void __launch_bounds__(256) dsm_mark_buckets_kernel(const __grid_constant__ DsmPlan plan,
+                                                               const unsigned int* __restrict__ cell_list,
+                                                               const unsigned int* __restrict__ counters,
+                                                               unsigned char* __restrict__ flags) {
+  const unsigned int n_cells = counters[CTR_DSM_LIST];
+  const int P = plan.P;
+  for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+    const unsigned int cell = cell_list[c];
+    const int i = static_cast<int>(cell % static_cast<unsigned int>(plan.rows));
+    const int jl = static_cast<int>(cell / static_cast<unsigned int>(plan.rows));
+    const int bi = i + plan.Pa, bj = plan.col_begin + jl - plan.gj0;
+    const int kbi0 = max(bi - P, 0) >> plan.Bshift, kbi1 = min(bi + P, plan.BR - 1) >> plan.Bshift;
+    const int kbj0 = max(bj - P, 0) >> plan.Bshift, kbj1 = min(bj + P, plan.BC - 1) >> plan.Bshift;
+    for (int kj = kbj0; kj <= kbj1; ++kj)
+      for (int ki = kbi0; ki <= kbi1; ++ki) flags[static_cast<size_t>(kj) * plan.KR + ki] = 1;
   }
 }
 
@@ -673,6 +712,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   AMB_CUDA(ctx, ctx->block_sums.reserve(static_cast<size_t>(scan_blocks) * sizeof(unsigned int)));
   AMB_CUDA(ctx, ctx->records.reserve(n * sizeof(PointRec)));
   AMB_CUDA(ctx, ctx->point_order.reserve(n * sizeof(unsigned int)));
+  AMB_CUDA(ctx, ctx->bucket_flags.reserve(nbk));
   AMB_CUDA(ctx, ctx->empty_cells.reserve(cells * sizeof(unsigned int)));
   st = ensure_counters(ctx);
   if (st != AMB_OK) return st;
@@ -686,6 +726,7 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   PointRec* rec = ctx->records.as<PointRec>();
 
   AMB_CUDA(ctx, cudaMemsetAsync(G, 0, g_elems * sizeof(unsigned int), s));
+  AMB_CUDA(ctx, cudaMemsetAsync(ctx->bucket_flags.ptr, 0, nbk, s));
   // only this stage's own slots: the sticky CHECK flags of earlier asynchronous calls stay until they are reported
   AMB_CUDA(ctx, cudaMemsetAsync(counters + CTR_DSM_LIST, 0, sizeof(unsigned int), s));
   AMB_CUDA(ctx, cudaMemsetAsync(counters + CTR_DSM_BINNED, 0, 4 * sizeof(unsigned int), s));  // [2..5]
@@ -697,16 +738,65 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
 
   const int stream_grid = kNumSMsB200 * 8;
   const HaloSource hs = halo ? *halo : HaloSource();
-  dsm_count_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n_own, plan, G, counters, hs);
+  // development switch: AMB_DSM_BINNING=direct keeps the one-level count + scatter of rounds 1-2 for A/B timing
+  static const bool direct_binning = [] {
+    const char* e = std::getenv("AMB_DSM_BINNING");
+    return e && e[0] == 'd';
+  }();
+  if (direct_binning) {
+    dsm_count_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n_own, plan, G, counters, hs);
+  } else {
+    // two-level binning (dsm_partition.inc): P1 bins, counts and groups every tile of points by coarse destination
+    PartPlan pp;
+    std::memset(&pp, 0, sizeof(pp));
+    pp.n_own = n_own;
+    pp.n_total = n;
+    // a destination = a band of bucket columns whose final records span ~24 MB at a uniform density (so that the
+    // one or two destinations in flight in P2 stay inside L2); at most kMaxCoarse bands
+    // (development / test knob AMB_DSM_PART_WINDOW: bytes per destination — small values exercise many destinations on
+    //  small maps)
+    static const size_t window_bytes = [] {
+      const char* e = std::getenv("AMB_DSM_PART_WINDOW");
+      const long long v = e ? std::atoll(e) : 0;
+      return v > 0 ? static_cast<size_t>(v) : size_t(24) << 20;
+    }();
+    int S = static_cast<int>(std::min<size_t>((n * sizeof(PointRec) + window_bytes - 1) / window_bytes, kMaxCoarse));
+    S = std::max(1, std::min(S, plan.KC));
+    pp.kj_per = (plan.KC + S - 1) / S;
+    pp.S = (plan.KC + pp.kj_per - 1) / pp.kj_per;
+    pp.n_tiles = static_cast<unsigned int>((n + kPartTile - 1) / kPartTile);
+    pp.n_groups = (pp.n_tiles + kFineTilesPerBlock - 1) / kFineTilesPerBlock;
+    AMB_CUDA(ctx, ctx->records_tmp.reserve(static_cast<size_t>(pp.n_tiles) * kPartTile * sizeof(PointRec)));
+    AMB_CUDA(ctx, ctx->tile_offsets.reserve(static_cast<size_t>(pp.S + 1) * pp.n_tiles * sizeof(unsigned short)));
+    const int part_grid = static_cast<int>(std::min<unsigned int>(pp.n_tiles, kNumSMsB200 * 4u));
+    dsm_partition_kernel<<<part_grid, kPartThreads, 0, s>>>(d_xyz, d_intensities, d_ids, plan, pp, G,
+                                                            ctx->records_tmp.as<PointRec>(),
+                                                            ctx->tile_offsets.as<unsigned short>(), counters, hs);
+    ctx->last_part_plan.assign(reinterpret_cast<const unsigned char*>(&pp),
+                               reinterpret_cast<const unsigned char*>(&pp) + sizeof(pp));
+  }
   scan_reduce_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(G), n_vec,
                                                  ctx->block_sums.as<unsigned int>());
   scan_spine_kernel<<<1, 1024, 0, s>>>(ctx->block_sums.as<unsigned int>(), scan_blocks);
   scan_apply_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(G), n_vec,
                                                 ctx->block_sums.as<unsigned int>());
-  dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_intensities, d_ids, n_own, plan, G, rec, hs);
-  dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
-                                                      ctx->point_order.as<unsigned int>());
-  ctx->dsm_launches += 6;
+  if (direct_binning) {
+    dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_intensities, d_ids, n_own, plan, G, rec, hs);
+  } else {
+    PartPlan pp;
+    std::memcpy(&pp, ctx->last_part_plan.data(), sizeof(pp));
+    dsm_fine_scatter_kernel<<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
+        plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
+  }
+  // Canonical order inside the buckets: Dsm orders only the buckets its warp-per-cell kernel will read (marked from the
+  // cell list after the gather); OrthoFromPcl's adaptive pass may read any bucket, so that mode orders all of them here.
+  unsigned char* bucket_flags = ctx->bucket_flags.as<unsigned char>();
+  if (mode == 1) {
+    dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
+                                                        ctx->point_order.as<unsigned int>(), nullptr);
+    ctx->dsm_launches += 1;
+  }
+  ctx->dsm_launches += 5;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BIN_END], s));
 
   // gather
@@ -797,6 +887,12 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
       } else {
         dsm_gather_kernel<<<ga.tiles_i * (tj1 - tj0), kGatherThreads, smem, s>>>(pc, ga);
       }
+      if (mode == 0) {
+        dsm_mark_buckets_kernel<<<kNumSMsB200 * 2, 256, 0, s>>>(pc, ga.cell_list, counters, bucket_flags);
+        dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
+                                                            ctx->point_order.as<unsigned int>(), bucket_flags);
+        ctx->dsm_launches += 2;
+      }
       dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(pc, ca);
       ctx->dsm_launches += 2;
       // slab-local columns of this group's tiles (tiles are aligned to GLOBAL columns)
@@ -834,6 +930,12 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
     ca.counters = counters;
     ca.dbg_count = ga.dbg_count;
     ca.dbg_level = ga.dbg_level;
+    if (mode == 0) {
+      dsm_mark_buckets_kernel<<<kNumSMsB200 * 2, 256, 0, s>>>(plan, ga.cell_list, counters, bucket_flags);
+      dsm_bucket_order_kernel<<<stream_grid, 256, 0, s>>>(G, static_cast<unsigned int>(nbk), rec,
+                                                          ctx->point_order.as<unsigned int>(), bucket_flags);
+      ctx->dsm_launches += 2;
+    }
     dsm_cell_kernel<<<kNumSMsB200 * 8, 256, 0, s>>>(plan, ca);
     ctx->dsm_launches += 1;
     AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_FILL_END], s));

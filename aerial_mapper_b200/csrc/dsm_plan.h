@@ -57,9 +57,13 @@ __device__ __forceinline__ double cell_y(const DsmPlan& p, int j_global) {
 // Fine bin (= nearest cell centre) of a shifted point; false if it lies outside the bin grid of this slab, i.e.
 // cannot reach any of its cells.  An off-by-one at a cell edge is harmless: membership is re-decided exactly by
 // d2 and every window carries half a cell of slack (see half_widths()).
+// (explicit fma: the two-level binning evaluates the column twice — once per pass — and must get the same bin)
+__device__ __forceinline__ double fine_bin_col(const DsmPlan& p, double py) {
+  return floor(fma(p.base_y - py, p.inv_res, 0.5)) - static_cast<double>(p.gj0);
+}
 __device__ __forceinline__ bool fine_bin(const DsmPlan& p, double px, double py, int* bi, int* bj) {
-  const double fi = floor((p.base_x - px) * p.inv_res + 0.5) + static_cast<double>(p.Pa);
-  const double fj = floor((p.base_y - py) * p.inv_res + 0.5) - static_cast<double>(p.gj0);
+  const double fi = floor(fma(p.base_x - px, p.inv_res, 0.5)) + static_cast<double>(p.Pa);
+  const double fj = fine_bin_col(p, py);
   if (!(fi >= 0.0 && fi < static_cast<double>(p.BR) && fj >= 0.0 && fj < static_cast<double>(p.BC))) return false;
   *bi = static_cast<int>(fi);
   *bj = static_cast<int>(fj);
