@@ -785,8 +785,20 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
   } else {
     PartPlan pp;
     std::memcpy(&pp, ctx->last_part_plan.data(), sizeof(pp));
-    dsm_fine_scatter_kernel<<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
-        plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
+    static const int in_flight = [] {  // development knob
+      const char* e = std::getenv("AMB_DSM_FINE_INFLIGHT");
+      return e ? std::atoi(e) : 2;
+    }();
+    if (in_flight == 4) {
+      dsm_fine_scatter_kernel<4><<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
+          plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
+    } else if (in_flight == 1) {
+      dsm_fine_scatter_kernel<1><<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
+          plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
+    } else {
+      dsm_fine_scatter_kernel<2><<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
+          plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
+    }
   }
   // Canonical order inside the buckets: Dsm orders only the buckets its warp-per-cell kernel will read (marked from the
   // cell list after the gather); OrthoFromPcl's adaptive pass may read any bucket, so that mode orders all of them here.

@@ -86,6 +86,8 @@ struct OrthoArgs {
   double nui_lo, nui_hi, nvi_lo, nvi_hi;  // sqrt(1 + bound^2)
   double dom_margin;                      // rad
   double dom_theta_in;                    // equidistant: every ray with angle-to-axis below this is imaged (else unused)
+  double dom_cos_in;                      // cos(dom_theta_in)
+  double dom_cos_margin, dom_sin_margin;  // cos / sin of dom_margin
   // --- exact re-evaluation (appended) ---
   const double* exact_data;               // device array [n_frames][8]: inverse(T_G_C) as the reference forms it —
                                           // conjugate quaternion (w, x, y, z), translation -(q^-1).rotate(t), pad
@@ -649,6 +651,11 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     }
   }
 
+  if (dominance) {
+    a.dom_cos_in = std::cos(a.dom_theta_in);
+    a.dom_cos_margin = std::cos(a.dom_margin);
+    a.dom_sin_margin = std::sin(a.dom_margin);
+  }
   const int tiles_i = (a.rows + OTI - 1) / OTI, tiles_j = (a.cols_slab + OTJ - 1) / OTJ;
   ctx->ortho_launches = 0;
   for (size_t f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {  // ascending chunks keep the frame order
