@@ -91,6 +91,7 @@ SYMBOLS = {
     "amb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "amb_comm_destroy": (C.c_int, [_P]),
     "amb_comm_set_exchange": (C.c_int, [_P, C.c_int]),
+    "amb_comm_last_exchange": (C.c_int, [_P]),
     "amb_comm_size": (C.c_int, [_P]),
     "amb_comm_rank": (C.c_int, [_P]),
     "amb_dsm_process_sharded_device": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double,

@@ -6,8 +6,10 @@
 // NCCL is loaded at run time (dlopen "libnccl.so.2"): the library keeps depending on the CUDA runtime only, a process
 // that already carries an NCCL (e.g. PyTorch's bundled one) shares it, and single-GPU users never need it.
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "amb_context.h"
@@ -136,6 +138,239 @@ __global__ void __launch_bounds__(256) dsm_halo_records_kernel(const double* __r
   }
 }
 
+
+// ---- fused compaction + transfer over NVLink peer memory (exchange mode "peer push") -------------------------------
+// With consecutive stripes each at least `reach` wide a rank's border points are needed by its two adjacent ranks only.
+// Instead of compacting into a local list and handing it to ncclSend/ncclRecv (a second kernel, NCCL's launch and
+// rendezvous latency: the halo step measured 0.36-0.38 ms for ~8 MB at N = 2 and N = 8 alike), the compaction kernel
+// stores every selected record STRAIGHT INTO THE NEIGHBOUR'S receive segment (its cudaMalloc'ed buffer, mapped here with
+// cudaIpcOpenMemHandle: the stores travel over NVLink / NVSwitch as they are produced), counts with local atomics, and
+// the last block to finish publishes {count, step stamp} in the neighbour's segment header with a system-scope
+// release.  The consumer runs halo_wait_kernel in front of its binning: two lanes spin (acquire, system scope) until
+// both headers carry this step's stamp.  Segments are double-buffered by step parity: a rank can only be two steps
+// ahead of a neighbour after having received that neighbour's halo of the step in between, which the neighbour sends
+// after it has finished reading the earlier one (stream order) — so a segment is never overwritten while it is read.
+struct HaloPushArgs {
+  unsigned char* seg_up;      // PEER memory: segment of rank - 1 that receives "from rank + 1"... i.e. from this rank (nullptr: no such rank)
+  unsigned char* seg_down;    // PEER memory: segment of rank + 1 that receives from this rank
+  unsigned int* counters;     // LOCAL: [0] up count, [1] down count, [2] blocks done
+  unsigned int capacity;      // records per segment
+  unsigned int stamp;         // step + 1
+};
+
+__device__ __forceinline__ void store_peer_record(double* dst, double x, double y, double z, unsigned long long id) {
+#ifdef AMB_CUDA_EMU  // tests/emu (the exchange itself never runs there: no NCCL, no peer memory)
+  dst[0] = x; dst[1] = y; dst[2] = z; dst[3] = __longlong_as_double(static_cast<long long>(id));
+#else
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(z),
+               "d"(__longlong_as_double(static_cast<long long>(id)))
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void store_release_sys(unsigned char* p, unsigned long long v) {
+#ifdef AMB_CUDA_EMU
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+#else
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned char* p) {
+#ifdef AMB_CUDA_EMU
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+#else
+  unsigned long long h;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(h) : "l"(p) : "memory");
+  return h;
+#endif
+}
+
+__device__ __forceinline__ void halo_push(bool take, int lane, unsigned char* seg, unsigned int* counter,
+                                          unsigned int capacity, double x, double y, double z, unsigned long long id) {
+  const unsigned int mask = __ballot_sync(0xffffffffu, take);
+  if (!mask) return;
+  const int leader = __ffs(mask) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(counter, static_cast<unsigned int>(__popc(mask)));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (take) {
+    const unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
+    if (slot < capacity) store_peer_record(reinterpret_cast<double*>(seg + 32) + 4 * static_cast<size_t>(slot), x, y, z, id);
+  }
+}
+
+__global__ void __launch_bounds__(256) dsm_halo_push_kernel(const double* __restrict__ xyz,
+                                                            const unsigned long long* __restrict__ ids, size_t n,
+                                                            double y_lo, double y_hi, double reach, double shift_y,
+                                                            HaloPushArgs a) {
+  const int lane = threadIdx.x & 31;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n_round = ((n + stride - 1) / stride) * stride;  // whole warps stay converged for the ballots
+  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < n_round; t += stride) {
+    bool up = false, down = false;
+    double x = 0, y = 0, z = 0;
+    unsigned long long id = 0;
+    if (t < n) {
+      y = xyz[3 * t + 1];
+      const double ys = y - shift_y;
+      up = a.seg_up && ys > y_hi - reach;    // column 0 is the max-y side: the previous rank's stripe lies beyond y_hi
+      down = a.seg_down && ys < y_lo + reach;
+      if (up || down) {
+        x = xyz[3 * t + 0];
+        z = xyz[3 * t + 2];
+        id = ids ? ids[t] : static_cast<unsigned long long>(t);
+      }
+    }
+    halo_push(up, lane, a.seg_up, a.counters + 0, a.capacity, x, y, z, id);
+    halo_push(down, lane, a.seg_down, a.counters + 1, a.capacity, x, y, z, id);
+  }
+  // publish: every thread's peer stores are fenced (system scope) before its block takes a ticket; the block that takes
+  // the last ticket has therefore "seen" all of them and releases the headers
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(a.counters + 2, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      const unsigned int c_up = atomicExch(a.counters + 0, 0u);    // (reset for the next step)
+      const unsigned int c_down = atomicExch(a.counters + 1, 0u);
+      atomicExch(a.counters + 2, 0u);
+      __threadfence_system();
+      const unsigned long long h_up = static_cast<unsigned long long>(c_up) | (static_cast<unsigned long long>(a.stamp) << 32);
+      const unsigned long long h_down = static_cast<unsigned long long>(c_down) | (static_cast<unsigned long long>(a.stamp) << 32);
+      if (a.seg_up) store_release_sys(a.seg_up, h_up);
+      if (a.seg_down) store_release_sys(a.seg_down, h_down);
+    }
+  }
+}
+
+// Lane 0 / 1: wait until the header of the segment filled by rank - 1 / rank + 1 carries this step's stamp.
+// Bounded (about two seconds of polling): a neighbour that never arrives raises the sticky halo flag instead of hanging
+// the GPU.
+__global__ void halo_wait_kernel(const unsigned char* seg_prev, const unsigned char* seg_next, unsigned int stamp,
+                                 unsigned int* counters) {
+  const unsigned char* seg = threadIdx.x == 0 ? seg_prev : seg_next;
+  if (threadIdx.x > 1 || !seg) return;
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned long long h = load_acquire_sys(seg);
+    if (static_cast<unsigned int>(h >> 32) == stamp) return;
+    if (clock64() - t0 > 4000000000ll) {
+      atomicExch(&counters[CTR_HALO_OVERFLOW], 1u);
+      return;
+    }
+    __nanosleep(200);
+  }
+}
+
+}  // namespace amb
+
+namespace amb {
+
+// Blob every rank contributes to the handle exchange of the peer-push halo.
+struct PeerBlob {
+  cudaIpcMemHandle_t handle;
+  long long pid;
+  unsigned long long raw_ptr;  // same-process contexts: the pointer itself
+  int device;
+  int ok;
+};
+
+static void peer_halo_release(amb_ctx* ctx) {
+  HaloPeer& hp = ctx->halo_peer;
+  if (hp.prev && hp.prev_ipc) cudaIpcCloseMemHandle(hp.prev);
+  if (hp.next && hp.next_ipc) cudaIpcCloseMemHandle(hp.next);
+  hp.prev = hp.next = nullptr;
+  hp.prev_ipc = hp.next_ipc = false;
+  if (hp.recv) cudaFree(hp.recv);
+  if (hp.counters) cudaFree(hp.counters);
+  hp.recv = nullptr;
+  hp.counters = nullptr;
+  hp.side_capacity = 0;
+  hp.enabled = false;
+}
+
+// (Re)allocate this rank's receive segments for `side_capacity` records per side and map the two neighbours'.
+// COLLECTIVE (one small ncclAllGather + a host synchronisation): runs on the first sharded call and whenever the
+// capacity grows — every rank passes the same halo_capacity, so every rank takes this branch in the same call.
+// On any failure anywhere, every rank agrees to keep the NCCL exchange.
+static int peer_halo_setup(amb_ctx* ctx, uint32_t side_capacity) {
+  HaloPeer& hp = ctx->halo_peer;
+  cudaStream_t s = ctx->stream;
+  const int nranks = ctx->comm_size, rank = ctx->comm_rank;
+  AMB_CUDA(ctx, cudaStreamSynchronize(s));  // nobody may still be reading / writing the segments that are replaced
+  peer_halo_release(ctx);
+  hp.tried = true;
+  const size_t side_bytes = 32 * (static_cast<size_t>(side_capacity) + 1);
+  PeerBlob mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.pid = static_cast<long long>(getpid());
+  mine.device = ctx->device;
+  mine.ok = 1;
+  if (cudaMalloc(reinterpret_cast<void**>(&hp.recv), 4 * side_bytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&hp.counters), 2 * 4 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(hp.recv, 0, 4 * side_bytes) != cudaSuccess ||
+      cudaMemset(hp.counters, 0, 2 * 4 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine.handle, hp.recv) != cudaSuccess) {
+    cudaGetLastError();
+    mine.ok = 0;
+  }
+  mine.raw_ptr = reinterpret_cast<unsigned long long>(hp.recv);
+  DeviceBuffer tmp;
+  AMB_CUDA(ctx, tmp.reserve(sizeof(PeerBlob) * (static_cast<size_t>(nranks) + 1)));
+  unsigned char* d = tmp.as<unsigned char>();
+  std::vector<PeerBlob> all(static_cast<size_t>(nranks));
+  AMB_CUDA(ctx, cudaMemcpyAsync(d, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+  int rc = nccl().all_gather(d, d + sizeof(PeerBlob), sizeof(PeerBlob), kNcclInt8,
+                             static_cast<nccl_comm_t>(ctx->nccl_comm), s);
+  if (rc != 0) return nccl_fail(ctx, rc, "ncclAllGather(peer halo handles)");
+  AMB_CUDA(ctx, cudaMemcpyAsync(all.data(), d + sizeof(PeerBlob), sizeof(PeerBlob) * nranks, cudaMemcpyDeviceToHost, s));
+  AMB_CUDA(ctx, cudaStreamSynchronize(s));
+  int ok = 1;
+  for (int r = 0; r < nranks; ++r) ok &= all[r].ok;
+  auto map_peer = [&](int r, unsigned char** out, bool* ipc) {
+    const PeerBlob& b = all[r];
+    if (b.pid == mine.pid) {  // another context of this process: plain peer access
+      if (b.device != ctx->device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return false;
+        cudaGetLastError();
+      }
+      *out = reinterpret_cast<unsigned char*>(b.raw_ptr);
+      *ipc = false;
+      return true;
+    }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    *out = static_cast<unsigned char*>(p);
+    *ipc = true;
+    return true;
+  };
+  if (ok && rank > 0 && !map_peer(rank - 1, &hp.prev, &hp.prev_ipc)) ok = 0;
+  if (ok && rank < nranks - 1 && !map_peer(rank + 1, &hp.next, &hp.next_ipc)) ok = 0;
+  // second round: everybody mapped its neighbours?
+  int* flag = reinterpret_cast<int*>(d);
+  std::vector<int> flags(static_cast<size_t>(nranks), 0);
+  AMB_CUDA(ctx, cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+  rc = nccl().all_gather(flag, flag + 1, sizeof(int), kNcclInt8, static_cast<nccl_comm_t>(ctx->nccl_comm), s);
+  if (rc != 0) return nccl_fail(ctx, rc, "ncclAllGather(peer halo status)");
+  AMB_CUDA(ctx, cudaMemcpyAsync(flags.data(), flag + 1, sizeof(int) * nranks, cudaMemcpyDeviceToHost, s));
+  AMB_CUDA(ctx, cudaStreamSynchronize(s));
+  tmp.release();
+  for (int r = 0; r < nranks; ++r) ok &= flags[r];
+  if (!ok) {
+    peer_halo_release(ctx);
+    hp.tried = true;
+    return AMB_OK;  // the NCCL exchange stays in charge
+  }
+  hp.side_capacity = side_capacity;
+  hp.enabled = true;
+  hp.step = 0;
+  return AMB_OK;
+}
+
 }  // namespace amb
 
 using namespace amb;
@@ -191,7 +426,7 @@ int amb_comm_init(amb_ctx* ctx, int rank, int nranks, const void* id128) {
 }
 
 int amb_comm_set_exchange(amb_ctx* ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 2) return AMB_ERR_INVALID_ARGUMENT;
+  if (!ctx || mode < 0 || mode > 3) return AMB_ERR_INVALID_ARGUMENT;
   ctx->halo_exchange_mode = mode;
   return AMB_OK;
 }
@@ -201,6 +436,7 @@ int amb_comm_destroy(amb_ctx* ctx) {
   if (ctx->nccl_comm && nccl().ok) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    peer_halo_release(ctx);
     nccl().comm_destroy(static_cast<nccl_comm_t>(ctx->nccl_comm));
   }
   ctx->nccl_comm = nullptr;
@@ -209,6 +445,7 @@ int amb_comm_destroy(amb_ctx* ctx) {
   return AMB_OK;
 }
 
+int amb_comm_last_exchange(const amb_ctx* ctx) { return ctx ? ctx->halo_last_exchange : 0; }
 int amb_comm_size(const amb_ctx* ctx) { return ctx ? ctx->comm_size : 0; }
 int amb_comm_rank(const amb_ctx* ctx) { return ctx ? ctx->comm_rank : -1; }
 
@@ -237,7 +474,7 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
   // half of the halo to the one rank that stages it.  Otherwise (narrow or irregular stripes) ONE ncclAllGather gives
   // every rank every halo.  The decision uses the stripes gathered at amb_comm_init: identical on all ranks.
   bool neighbours = ctx->halo_exchange_mode != 1;
-  if (ctx->halo_exchange_mode == 0) {
+  if (ctx->halo_exchange_mode == 0 || ctx->halo_exchange_mode == 3) {
     const double reach_cols = reach / ctx->geom.resolution;
     for (int r = 0; r < nranks && neighbours; ++r) {
       const int32_t b = ctx->comm_stripes[2 * r], e = ctx->comm_stripes[2 * r + 1];
@@ -249,11 +486,53 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
   halo.capacity = halo_capacity;
   halo.seg_bytes = seg_bytes;
   if (neighbours) {
-    // send: [up | down], recv: [from rank - 1 | from rank + 1]; each list holds ONE side of the halo: half the capacity
+    // each list holds ONE side of the halo: half the capacity
     const uint32_t side_capacity = halo_capacity / 2 + 1;
     const size_t side_bytes = 32 * (static_cast<size_t>(side_capacity) + 1);
     halo.capacity = side_capacity;
     halo.seg_bytes = side_bytes;
+    HaloPeer& hp = ctx->halo_peer;
+    if (!hp.tried) {
+      const char* e = std::getenv("AMB_HALO_PEER");  // development switch: AMB_HALO_PEER=0 keeps ncclSend/ncclRecv
+      hp.disabled = e && e[0] == '0';
+    }
+    // (collective, see peer_halo_setup: first sharded call, or the capacity grew — the same on every rank)
+    if (ctx->halo_exchange_mode != 3 && !hp.disabled && (!hp.tried || (hp.enabled && side_capacity > hp.side_capacity))) {
+      hp.tried_capacity = side_capacity;
+      st = peer_halo_setup(ctx, side_capacity);
+      if (st != AMB_OK) return st;
+    }
+    if (hp.enabled && ctx->halo_exchange_mode != 3) {
+      // peer push: the compaction kernel stores into the neighbours' segments of this step's parity and publishes the
+      // counts; halo_wait_kernel holds the binning back until both neighbours have published theirs
+      const size_t peer_side_bytes = 32 * (static_cast<size_t>(hp.side_capacity) + 1);
+      const unsigned int parity = static_cast<unsigned int>(hp.step & 1u);
+      const unsigned int stamp = static_cast<unsigned int>(hp.step + 1);
+      ++hp.step;
+      HaloPushArgs pa;
+      // segment layout of every rank: [parity][0 = filled by rank - 1 | 1 = filled by rank + 1]
+      pa.seg_up = hp.prev ? hp.prev + (2 * parity + 1) * peer_side_bytes : nullptr;    // I am rank - 1's "rank + 1"
+      pa.seg_down = hp.next ? hp.next + (2 * parity + 0) * peer_side_bytes : nullptr;  // I am rank + 1's "rank - 1"
+      pa.counters = hp.counters + 4 * parity;
+      pa.capacity = side_capacity;
+      pa.stamp = stamp;
+      const int grid = n_local > 0 ? kNumSMsB200 * 8 : 1;
+      dsm_halo_push_kernel<<<grid, 256, 0, s>>>(d_xyz, reinterpret_cast<const unsigned long long*>(d_ids), n_local, y_lo,
+                                                y_hi, reach, center_easting, pa);
+      AMB_CUDA(ctx, cudaGetLastError());
+      st = ensure_counters(ctx);
+      if (st != AMB_OK) return st;
+      unsigned char* mine = hp.recv + 2 * parity * peer_side_bytes;
+      halo_wait_kernel<<<1, 32, 0, s>>>(rank > 0 ? mine : nullptr, rank < nranks - 1 ? mine + peer_side_bytes : nullptr,
+                                        stamp, ctx->counters.as<unsigned int>());
+      AMB_CUDA(ctx, cudaGetLastError());
+      ctx->halo_last_exchange = 4;
+      halo.gathered = mine;
+      halo.seg_bytes = peer_side_bytes;
+      halo.nranks = 2;
+      halo.my_rank = -1;  // both segments are foreign (a missing neighbour's header stays {0, 0}: an empty list)
+    } else {
+    // send: [up | down], recv: [from rank - 1 | from rank + 1]
     AMB_CUDA(ctx, ctx->halo_send.reserve(2 * side_bytes));
     AMB_CUDA(ctx, ctx->halo_recv.reserve(2 * side_bytes));
     unsigned char* send = ctx->halo_send.as<unsigned char>();
@@ -276,9 +555,11 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
     if (rc == 0 && rank < nranks - 1) rc = nccl().recv(recv + side_bytes, side_bytes, kNcclInt8, rank + 1, comm, s);
     const int rc_end = nccl().group_end();
     if (rc != 0 || rc_end != 0) return nccl_fail(ctx, rc != 0 ? rc : rc_end, "ncclSend/ncclRecv (halo)");
+    ctx->halo_last_exchange = 2;
     halo.gathered = recv;
     halo.nranks = 2;
     halo.my_rank = -1;  // both segments are foreign
+    }
   } else {
     AMB_CUDA(ctx, ctx->halo_send.reserve(seg_bytes));
     AMB_CUDA(ctx, ctx->halo_recv.reserve(seg_bytes * nranks));
@@ -294,6 +575,7 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
     const int rc = nccl().all_gather(send, ctx->halo_recv.ptr, seg_bytes, kNcclInt8,
                                      static_cast<nccl_comm_t>(ctx->nccl_comm), s);
     if (rc != 0) return nccl_fail(ctx, rc, "ncclAllGather");
+    ctx->halo_last_exchange = 1;
     halo.gathered = ctx->halo_recv.as<unsigned char>();
     halo.nranks = nranks;
     halo.my_rank = rank;

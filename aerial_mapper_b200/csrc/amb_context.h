@@ -126,6 +126,19 @@ struct CompactMirror {
 // The neighbours' border halos as delivered by the all-gather (amb_comm.cu): nranks segments of seg_bytes, each a 32-byte
 // header {uint32 count, ...} followed by `capacity` 32-byte records {x, y, z, id}.  The binning kernels read them
 // after the rank's own points; the segment of the rank itself is skipped (those points are already local).
+// Peer-push halo exchange (amb_comm.cu): this rank's receive segments [parity 0/1][from rank - 1 | from rank + 1] and the
+// mapped pointers to the two neighbours' segments.
+struct HaloPeer {
+  bool enabled = false, tried = false, disabled = false;
+  unsigned char* recv = nullptr;       // own, cudaMalloc: 4 segments of 32 * (side_capacity + 1) bytes
+  unsigned int* counters = nullptr;    // own: [parity][up count, down count, blocks done, -]
+  unsigned char* prev = nullptr;       // rank - 1's `recv`, mapped (cudaIpcOpenMemHandle or same-process peer access)
+  unsigned char* next = nullptr;
+  bool prev_ipc = false, next_ipc = false;
+  uint32_t side_capacity = 0, tried_capacity = 0;
+  uint64_t step = 0;
+};
+
 struct HaloSource {
   const unsigned char* gathered = nullptr;
   int nranks = 0, my_rank = 0;
@@ -186,6 +199,8 @@ struct amb_ctx {
   std::vector<int32_t> comm_stripes;   // [2 * nranks]: col_begin, col_end of every member (gathered by amb_comm_init)
   int halo_exchange_mode = 0;          // 0 auto, 1 all-gather, 2 neighbours (amb_comm_set_exchange)
   amb::DeviceBuffer halo_send, halo_recv;
+  amb::HaloPeer halo_peer;
+  int halo_last_exchange = 0;          // what the last sharded call used: 1 all-gather, 2 ncclSend/ncclRecv, 4 peer push
   int dsm_precision = AMB_DSM_F32;  // amb_dsm_set_precision: arithmetic of the tile gather's weights and sums
   bool dsm_debug_valid = false;
   int64_t last_points_binned = 0, last_cells_empty = 0;

@@ -526,9 +526,11 @@ def run_ours(args):
                       "interpolation_radius": 1, "dsm_precision": lib_prec if do_dsm else None,
                       "sharding": ("column stripes x%d; cloud sharded by stripe; border halos exchanged inside the library on "
                                    "its own stream (%s); layers stay sharded"
-                                   % (world, {0: "auto: ncclSend/ncclRecv with the two adjacent ranks, one ncclAllGather for "
-                                                 "stripes narrower than the reach", 1: "one ncclAllGather",
-                                              2: "ncclSend/ncclRecv with the two adjacent ranks"}[exchange_mode]))
+                                   % (world, {0: "not a DSM workload", 1: "one ncclAllGather",
+                                              2: "ncclSend/ncclRecv with the two adjacent ranks",
+                                              4: "peer push: the compaction kernel stores into the two adjacent ranks' "
+                                                 "segments over NVLink peer memory, no collective call in the step"}
+                                   [int(amb.lib().amb_comm_last_exchange(ctx))]))
                       if world > 1 else "single GPU",
                       "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W * channels) / 1e9),
                       "timed_region": "K steps enqueued back to back, one synchronisation at the end"},

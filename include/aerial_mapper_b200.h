@@ -222,10 +222,17 @@ int amb_dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const uint64_t* d_id
 int amb_comm_unique_id(void* id128);
 int amb_comm_init(amb_ctx* ctx, int rank, int nranks, const void* id128);
 int amb_comm_destroy(amb_ctx* ctx);
-/* How amb_dsm_process_sharded* exchanges the border halos: 0 (default) = automatic — two ncclSend/ncclRecv pairs with the
- * adjacent ranks when the stripes are consecutive and each at least amb_dsm_halo_reach wide, else one ncclAllGather;
- * 1 = always the all-gather; 2 = always neighbours (the caller guarantees the condition).  Same value on every rank. */
+/* How amb_dsm_process_sharded* exchanges the border halos: 0 (default) = automatic — with consecutive stripes, each at
+ * least amb_dsm_halo_reach wide, only the two adjacent ranks need a rank's border points: the compaction kernel then
+ * stores them straight into the neighbours' receive segments over NVLink peer memory (cudaIpc-mapped; counts and a step
+ * stamp published with a system-scope release, the binning waits on them: no collective call in the step), or, where peer
+ * mapping is unavailable, two ncclSend/ncclRecv pairs move the compacted lists; narrow or irregular stripes use one
+ * ncclAllGather.  1 = always the all-gather; 2 = always neighbours (the caller guarantees the condition); 3 = neighbours
+ * through ncclSend/ncclRecv only (no peer push).  Same value on every rank.  The first sharded call (and a later one
+ * with a larger halo_capacity) exchanges the memory handles: a collective with one host synchronisation. */
 int amb_comm_set_exchange(amb_ctx* ctx, int mode);
+/* What the last amb_dsm_process_sharded* call used: 1 all-gather, 2 ncclSend/ncclRecv, 4 peer push (0: none yet). */
+int amb_comm_last_exchange(const amb_ctx* ctx);
 int amb_comm_size(const amb_ctx* ctx);
 int amb_comm_rank(const amb_ctx* ctx);
 /* Dsm::process on a cloud that arrives sharded by stripe, the exchange included: this rank's points (device memory, global

@@ -249,6 +249,16 @@ inline float __int_as_float(int v) {
   return f;
 }
 inline void __threadfence_system() {}
+inline long long clock64() { return 0; }
+inline void __nanosleep(unsigned int) {}
+// inter-process peer memory: not available on the emulation (the peer-push halo exchange of amb_comm.cu stays off)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+constexpr unsigned int cudaIpcMemLazyEnablePeerAccess = 1;
+constexpr cudaError_t cudaErrorPeerAccessAlreadyEnabled = 704;
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned int) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned int) { return cudaErrorInvalidValue; }
 inline void __threadfence() {}
 
 inline void __syncthreads() { emu::sync_block(); }
