@@ -14,6 +14,7 @@
 
 #include "amb_context.h"
 #include "dsm_plan.h"
+#include "halo_push.h"
 
 namespace amb {
 
@@ -141,108 +142,17 @@ __global__ void __launch_bounds__(256) dsm_halo_records_kernel(const double* __r
 
 // ---- fused compaction + transfer over NVLink peer memory (exchange mode "peer push") -------------------------------
 // With consecutive stripes each at least `reach` wide a rank's border points are needed by its two adjacent ranks only.
-// Instead of compacting into a local list and handing it to ncclSend/ncclRecv (a second kernel, NCCL's launch and
-// rendezvous latency: the halo step measured 0.36-0.38 ms for ~8 MB at N = 2 and N = 8 alike), the compaction kernel
-// stores every selected record STRAIGHT INTO THE NEIGHBOUR'S receive segment (its cudaMalloc'ed buffer, mapped here with
-// cudaIpcOpenMemHandle: the stores travel over NVLink / NVSwitch as they are produced), counts with local atomics, and
-// the last block to finish publishes {count, step stamp} in the neighbour's segment header with a system-scope
-// release.  The consumer runs halo_wait_kernel in front of its binning: two lanes spin (acquire, system scope) until
-// both headers carry this step's stamp.  Segments are double-buffered by step parity: a rank can only be two steps
+// Instead of a compaction pass over the rank's points followed by ncclSend/ncclRecv (a second read of the cloud, a second
+// kernel, NCCL's launch and rendezvous latency: the halo step measured 0.36-0.38 ms for ~8 MB at N = 2 and N = 8 alike),
+// the binning's own partition kernel (dsm_partition.inc, which reads every point anyway) stores every border record
+// STRAIGHT INTO THE NEIGHBOUR'S receive segment (its cudaMalloc'ed buffer, mapped here with cudaIpcOpenMemHandle: the
+// stores travel over NVLink / NVSwitch as they are produced), counts with local atomics, and its last block publishes
+// {count, step stamp} in the neighbour's segment header with a system-scope release (halo_push.h).  The consumer runs
+// halo_wait_kernel in front of the binning of the incoming halos: two lanes spin (acquire, system scope) until both
+// headers carry this step's stamp.  Segments are double-buffered by step parity: a rank can only be two steps
 // ahead of a neighbour after having received that neighbour's halo of the step in between, which the neighbour sends
 // after it has finished reading the earlier one (stream order) — so a segment is never overwritten while it is read.
-struct HaloPushArgs {
-  unsigned char* seg_up;      // PEER memory: segment of rank - 1 that receives "from rank + 1"... i.e. from this rank (nullptr: no such rank)
-  unsigned char* seg_down;    // PEER memory: segment of rank + 1 that receives from this rank
-  unsigned int* counters;     // LOCAL: [0] up count, [1] down count, [2] blocks done
-  unsigned int capacity;      // records per segment
-  unsigned int stamp;         // step + 1
-};
-
-__device__ __forceinline__ void store_peer_record(double* dst, double x, double y, double z, unsigned long long id) {
-#ifdef AMB_CUDA_EMU  // tests/emu (the exchange itself never runs there: no NCCL, no peer memory)
-  dst[0] = x; dst[1] = y; dst[2] = z; dst[3] = __longlong_as_double(static_cast<long long>(id));
-#else
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(z),
-               "d"(__longlong_as_double(static_cast<long long>(id)))
-               : "memory");
-#endif
-}
-__device__ __forceinline__ void store_release_sys(unsigned char* p, unsigned long long v) {
-#ifdef AMB_CUDA_EMU
-  *reinterpret_cast<volatile unsigned long long*>(p) = v;
-#else
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#endif
-}
-__device__ __forceinline__ unsigned long long load_acquire_sys(const unsigned char* p) {
-#ifdef AMB_CUDA_EMU
-  return *reinterpret_cast<const volatile unsigned long long*>(p);
-#else
-  unsigned long long h;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(h) : "l"(p) : "memory");
-  return h;
-#endif
-}
-
-__device__ __forceinline__ void halo_push(bool take, int lane, unsigned char* seg, unsigned int* counter,
-                                          unsigned int capacity, double x, double y, double z, unsigned long long id) {
-  const unsigned int mask = __ballot_sync(0xffffffffu, take);
-  if (!mask) return;
-  const int leader = __ffs(mask) - 1;
-  unsigned int base = 0;
-  if (lane == leader) base = atomicAdd(counter, static_cast<unsigned int>(__popc(mask)));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (take) {
-    const unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
-    if (slot < capacity) store_peer_record(reinterpret_cast<double*>(seg + 32) + 4 * static_cast<size_t>(slot), x, y, z, id);
-  }
-}
-
-__global__ void __launch_bounds__(256) dsm_halo_push_kernel(const double* __restrict__ xyz,
-                                                            const unsigned long long* __restrict__ ids, size_t n,
-                                                            double y_lo, double y_hi, double reach, double shift_y,
-                                                            HaloPushArgs a) {
-  const int lane = threadIdx.x & 31;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  const size_t n_round = ((n + stride - 1) / stride) * stride;  // whole warps stay converged for the ballots
-  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < n_round; t += stride) {
-    bool up = false, down = false;
-    double x = 0, y = 0, z = 0;
-    unsigned long long id = 0;
-    if (t < n) {
-      y = xyz[3 * t + 1];
-      const double ys = y - shift_y;
-      up = a.seg_up && ys > y_hi - reach;    // column 0 is the max-y side: the previous rank's stripe lies beyond y_hi
-      down = a.seg_down && ys < y_lo + reach;
-      if (up || down) {
-        x = xyz[3 * t + 0];
-        z = xyz[3 * t + 2];
-        id = ids ? ids[t] : static_cast<unsigned long long>(t);
-      }
-    }
-    halo_push(up, lane, a.seg_up, a.counters + 0, a.capacity, x, y, z, id);
-    halo_push(down, lane, a.seg_down, a.counters + 1, a.capacity, x, y, z, id);
-  }
-  // publish: every thread's peer stores are fenced (system scope) before its block takes a ticket; the block that takes
-  // the last ticket has therefore "seen" all of them and releases the headers
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(a.counters + 2, 1u);
-    if (ticket == gridDim.x - 1) {
-      __threadfence();
-      const unsigned int c_up = atomicExch(a.counters + 0, 0u);    // (reset for the next step)
-      const unsigned int c_down = atomicExch(a.counters + 1, 0u);
-      atomicExch(a.counters + 2, 0u);
-      __threadfence_system();
-      const unsigned long long h_up = static_cast<unsigned long long>(c_up) | (static_cast<unsigned long long>(a.stamp) << 32);
-      const unsigned long long h_down = static_cast<unsigned long long>(c_down) | (static_cast<unsigned long long>(a.stamp) << 32);
-      if (a.seg_up) store_release_sys(a.seg_up, h_up);
-      if (a.seg_down) store_release_sys(a.seg_down, h_down);
-    }
-  }
-}
-
+//
 // Lane 0 / 1: wait until the header of the segment filled by rank - 1 / rank + 1 carries this step's stamp.
 // Bounded (about two seconds of polling): a neighbour that never arrives raises the sticky halo flag instead of hanging
 // the GPU.
@@ -265,6 +175,14 @@ __global__ void halo_wait_kernel(const unsigned char* seg_prev, const unsigned c
 }  // namespace amb
 
 namespace amb {
+
+int halo_wait_launch(amb_ctx* ctx, const HaloPush& push) {
+  const int st = ensure_counters(ctx);
+  if (st != AMB_OK) return st;
+  halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(push.wait_prev, push.wait_next, push.stamp, ctx->counters.as<unsigned int>());
+  AMB_CUDA(ctx, cudaGetLastError());
+  return AMB_OK;
+}
 
 // Blob every rank contributes to the handle exchange of the peer-push halo.
 struct PeerBlob {
@@ -483,6 +401,8 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
     }
   }
   HaloSource halo;
+  HaloPush push;
+  bool use_push = false;
   halo.capacity = halo_capacity;
   halo.seg_bytes = seg_bytes;
   if (neighbours) {
@@ -503,29 +423,27 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
       if (st != AMB_OK) return st;
     }
     if (hp.enabled && ctx->halo_exchange_mode != 3) {
-      // peer push: the compaction kernel stores into the neighbours' segments of this step's parity and publishes the
-      // counts; halo_wait_kernel holds the binning back until both neighbours have published theirs
+      // peer push: the partition kernel of the binning (dsm_run) stores the border records into the neighbours' segments of
+      // this step's parity while it bins the rank's own points and publishes the counts; halo_wait_kernel then holds the
+      // binning of the incoming halos back until both neighbours have published theirs
       const size_t peer_side_bytes = 32 * (static_cast<size_t>(hp.side_capacity) + 1);
       const unsigned int parity = static_cast<unsigned int>(hp.step & 1u);
       const unsigned int stamp = static_cast<unsigned int>(hp.step + 1);
       ++hp.step;
-      HaloPushArgs pa;
       // segment layout of every rank: [parity][0 = filled by rank - 1 | 1 = filled by rank + 1]
-      pa.seg_up = hp.prev ? hp.prev + (2 * parity + 1) * peer_side_bytes : nullptr;    // I am rank - 1's "rank + 1"
-      pa.seg_down = hp.next ? hp.next + (2 * parity + 0) * peer_side_bytes : nullptr;  // I am rank + 1's "rank - 1"
-      pa.counters = hp.counters + 4 * parity;
-      pa.capacity = side_capacity;
-      pa.stamp = stamp;
-      const int grid = n_local > 0 ? kNumSMsB200 * 8 : 1;
-      dsm_halo_push_kernel<<<grid, 256, 0, s>>>(d_xyz, reinterpret_cast<const unsigned long long*>(d_ids), n_local, y_lo,
-                                                y_hi, reach, center_easting, pa);
-      AMB_CUDA(ctx, cudaGetLastError());
-      st = ensure_counters(ctx);
-      if (st != AMB_OK) return st;
+      push.seg_up = hp.prev ? hp.prev + (2 * parity + 1) * peer_side_bytes : nullptr;    // I am rank - 1's "rank + 1"
+      push.seg_down = hp.next ? hp.next + (2 * parity + 0) * peer_side_bytes : nullptr;  // I am rank + 1's "rank - 1"
+      push.counters = hp.counters + 4 * parity;
+      push.capacity = side_capacity;
+      push.stamp = stamp;
+      push.y_lo = y_lo;
+      push.y_hi = y_hi;
+      push.reach = reach;
+      push.shift_y = center_easting;
       unsigned char* mine = hp.recv + 2 * parity * peer_side_bytes;
-      halo_wait_kernel<<<1, 32, 0, s>>>(rank > 0 ? mine : nullptr, rank < nranks - 1 ? mine + peer_side_bytes : nullptr,
-                                        stamp, ctx->counters.as<unsigned int>());
-      AMB_CUDA(ctx, cudaGetLastError());
+      push.wait_prev = rank > 0 ? mine : nullptr;
+      push.wait_next = rank < nranks - 1 ? mine + peer_side_bytes : nullptr;
+      use_push = true;
       ctx->halo_last_exchange = 4;
       halo.gathered = mine;
       halo.seg_bytes = peer_side_bytes;
@@ -583,7 +501,7 @@ int amb_dsm_process_sharded_device(amb_ctx* ctx, const double* d_xyz, const uint
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], s));  // "h2d" slot of the timings = the halo step
   ctx->dsm_had_h2d = true;
   st = dsm_run(ctx, d_xyz, reinterpret_cast<const unsigned long long*>(d_ids), n_local, interpolation_radius,
-               center_easting, center_northing, 0, nullptr, &halo);
+               center_easting, center_northing, 0, nullptr, &halo, use_push ? &push : nullptr);
   ctx->dsm_timed = (st == AMB_OK);
   return st;
 }

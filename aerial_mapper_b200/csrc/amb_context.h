@@ -180,7 +180,6 @@ struct amb_ctx {
   amb::DeviceBuffer records;      // bucket-sorted 32-byte point records
   amb::DeviceBuffer records_tmp;  // two-level binning: the points as 32-byte records, tile by tile, grouped by coarse destination
   amb::DeviceBuffer tile_offsets; // ... and the uint16 run starts, [(S + 1)][n_tiles]
-  std::vector<unsigned char> last_part_plan;
   amb::DeviceBuffer point_order;  // uint32 per record: canonical (original-index) visiting order inside a bucket
   amb::DeviceBuffer bucket_flags; // one byte per bucket: the warp-per-cell kernel will read it (dsm_mark_buckets_kernel)
   amb::DeviceBuffer bin_starts;   // uint32 G[nb + 2]
@@ -223,6 +222,8 @@ struct amb_ctx {
 
 namespace amb {
 
+struct HaloPush;  // halo_push.h
+
 inline int fail(amb_ctx* ctx, cudaError_t e, const char* what) {
   if (ctx) {
     ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -251,7 +252,7 @@ void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
             int32_t interpolation_radius, double center_easting, double center_northing, int mode = 0,
-            const int* d_intensities = nullptr, const HaloSource* halo = nullptr);
+            const int* d_intensities = nullptr, const HaloSource* halo = nullptr, const HaloPush* push = nullptr);
 int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n, double y_lo,
                      double y_hi, double reach, double center_easting, double* d_out_xyz,
                      unsigned long long* d_out_ids, unsigned int capacity, unsigned int* d_count);

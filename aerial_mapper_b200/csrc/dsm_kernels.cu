@@ -36,6 +36,7 @@
 
 #include "amb_context.h"
 #include "dsm_plan.h"
+#include "halo_push.h"
 
 namespace amb {
 
@@ -99,45 +100,6 @@ __device__ __forceinline__ const double* halo_record(const HaloSource& h, size_t
   return reinterpret_cast<const double*>(seg + 32) + 4 * static_cast<size_t>(k);
 }
 
-__global__ void __launch_bounds__(256) dsm_count_kernel(const double* __restrict__ xyz, size_t n, DsmPlan plan,
-                                                        unsigned int* __restrict__ G,
-                                                        unsigned int* __restrict__ counters, HaloSource halo) {
-  unsigned int local = 0;
-  if (halo.nranks) {  // the neighbours' border points (sharded cloud)
-    const size_t slots = static_cast<size_t>(halo.nranks) * halo.capacity;
-    for (size_t s = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; s < slots;
-         s += static_cast<size_t>(gridDim.x) * blockDim.x) {
-      const double* r = halo_record(halo, s);
-      if (!r) continue;
-      int bi, bj;
-      if (fine_bin(plan, r[0] - plan.shift_x, r[1] - plan.shift_y, &bi, &bj)) {
-        const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
-                               static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
-        atomicAdd(&G[b + 2], 1u);
-        ++local;
-      }
-    }
-    if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < halo.nranks) {  // a truncated halo anywhere is an error everywhere
-      const unsigned int c = *reinterpret_cast<const unsigned int*>(halo.gathered + threadIdx.x * halo.seg_bytes);
-      if (c > halo.capacity) atomicExch(&counters[CTR_HALO_OVERFLOW], 1u);
-    }
-  }
-  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < n;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const double px = xyz[3 * t + 0] - plan.shift_x;
-    const double py = xyz[3 * t + 1] - plan.shift_y;
-    int bi, bj;
-    if (fine_bin(plan, px, py, &bi, &bj)) {
-      const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
-                             static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
-      atomicAdd(&G[b + 2], 1u);
-      ++local;
-    }
-  }
-  // total binned points (stats only): warp-aggregate, one atomic per warp
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counters[CTR_DSM_BINNED], local);
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // K2: inclusive scan (reduce / spine / apply).
@@ -228,76 +190,7 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(uint4* __restrict__ dat
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: scatter.  G[b + 1] holds start(b) before this kernel; atomicAdd turns it into start(b + 1), i.e.
-// afterwards G[b] = start(b) for b in [0, nbuckets].
-__global__ void __launch_bounds__(256) dsm_scatter_kernel(const double* __restrict__ xyz,
-                                                          const int* __restrict__ intensities,
-                                                          const unsigned long long* __restrict__ ids, size_t n,
-                                                          DsmPlan plan, unsigned int* __restrict__ G,
-                                                          PointRec* __restrict__ rec, HaloSource halo) {
-  if (halo.nranks) {
-    const size_t slots = static_cast<size_t>(halo.nranks) * halo.capacity;
-    for (size_t s = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; s < slots;
-         s += static_cast<size_t>(gridDim.x) * blockDim.x) {
-      const double* r = halo_record(halo, s);
-      if (!r) continue;
-      const double px = r[0] - plan.shift_x, py = r[1] - plan.shift_y;
-      int bi, bj;
-      if (fine_bin(plan, px, py, &bi, &bj)) {
-        const unsigned int b = static_cast<unsigned int>(bi >> plan.Bshift) +
-                               static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
-        const unsigned int code = (static_cast<unsigned int>(bi) << 4) | (static_cast<unsigned int>(bj) & 15u);
-        const unsigned long long id = static_cast<unsigned long long>(__double_as_longlong(r[3])) & 0xffffffffull;
-        store_rec(rec + atomicAdd(&G[b + 1], 1u), px, py, r[2], id | (static_cast<unsigned long long>(code) << 32));
-      }
-    }
-  }
-  // Latency-bound chain per point (load -> atomic with return -> store): keep kBatch points in flight per thread.
-  constexpr int kBatch = 4;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t0 < n; t0 += stride * kBatch) {
-    double px[kBatch], py[kBatch], pz[kBatch];
-    unsigned int bucket[kBatch], pos[kBatch], code[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const size_t t = t0 + u * stride;
-      if (t < n) {
-        px[u] = xyz[3 * t + 0];
-        py[u] = xyz[3 * t + 1];
-        // OrthoFromPcl interpolates the intensities: z = double(intensities[i]) (ortho-from-pcl.cc:33)
-        pz[u] = intensities ? static_cast<double>(intensities[t]) : xyz[3 * t + 2];
-      } else {
-        px[u] = py[u] = pz[u] = __longlong_as_double(0x7ff8000000000000ll);  // NaN: fine_bin rejects it
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      px[u] -= plan.shift_x;
-      py[u] -= plan.shift_y;
-      int bi, bj;
-      bucket[u] = 0xffffffffu;
-      code[u] = 0u;
-      if (fine_bin(plan, px[u], py[u], &bi, &bj)) {
-        bucket[u] = static_cast<unsigned int>(bi >> plan.Bshift) +
-                    static_cast<unsigned int>(bj >> plan.Bshift) * static_cast<unsigned int>(plan.KR);
-        code[u] = (static_cast<unsigned int>(bi) << 4) | (static_cast<unsigned int>(bj) & 15u);  // PointRec::idx, high word
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      if (bucket[u] != 0xffffffffu) pos[u] = atomicAdd(&G[bucket[u] + 1], 1u);
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      if (bucket[u] != 0xffffffffu) {
-        // the canonical-order key: position in the caller's array, or the caller's own (global) point id when the
-        // cloud arrives sharded — so that a stripe sees the same order as the undivided map
-        const size_t t = t0 + u * stride;
-        const unsigned long long id = ids ? (ids[t] & 0xffffffffull) : static_cast<unsigned long long>(t);
-        store_rec(rec + pos[u], px[u], py[u], pz[u], id | (static_cast<unsigned long long>(code[u]) << 32));
-      }
-  }
-}
-
+// K1 / K3: two-level binning
 #include "dsm_partition.inc"
 
 // K3b: canonical order inside every bucket (ascending original index = what a stable sort would give), as an
@@ -633,11 +526,12 @@ int dsm_extract_halo(amb_ctx* ctx, const double* d_xyz, const unsigned long long
 
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
             int32_t interpolation_radius, double center_easting, double center_northing, int mode,
-            const int* d_intensities, const HaloSource* halo) {
+            const int* d_intensities, const HaloSource* halo, const HaloPush* push) {
   const amb_geometry& g = ctx->geom;
   if (n == 0 && !halo) return AMB_ERR_EMPTY;
   const size_t n_own = n;
-  if (halo) n += static_cast<size_t>(halo->nranks) * halo->capacity;  // upper bound of the records this rank bins
+  // with halos: [own points | padding to a whole tile | halo slots] — an upper bound of the records this rank bins
+  if (halo) n = ((n_own + 2047) / 2048) * 2048 + static_cast<size_t>(halo->nranks) * halo->capacity;
   if (interpolation_radius < 1 || n >= size_t(0xffffffffu)) return AMB_ERR_INVALID_ARGUMENT;
   const int out_layer = mode == 1 ? AMB_LAYER_ORTHO : AMB_LAYER_ELEVATION;  // ortho-from-pcl.cc:51 / dsm.cc:116
   int st = ensure_layer(ctx, out_layer);
@@ -738,68 +632,64 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
 
   const int stream_grid = kNumSMsB200 * 8;
   const HaloSource hs = halo ? *halo : HaloSource();
-  // development switch: AMB_DSM_BINNING=direct keeps the one-level count + scatter of rounds 1-2 for A/B timing
-  static const bool direct_binning = [] {
-    const char* e = std::getenv("AMB_DSM_BINNING");
-    return e && e[0] == 'd';
+  // two-level binning (dsm_partition.inc): P1 bins, counts and groups every tile of points by coarse destination
+  PartPlan pp;
+  std::memset(&pp, 0, sizeof(pp));
+  pp.n_own = n_own;
+  pp.halo_base = halo ? ((n_own + kPartTile - 1) / kPartTile) * kPartTile : n_own;   // halo slots start a new tile
+  pp.n_total = n;
+  // a destination = a band of bucket columns whose final records span ~48 MB at a uniform density (so that the one or
+  // two destinations in flight in P2 stay inside the 126 MB L2; measured at 50 M points: 8 MB 1.68 ms, 24 MB 1.47,
+  // 48 MB 1.38, 96 MB 1.36 for the whole binning stage); at most kMaxCoarse bands
+  // (test knob AMB_DSM_PART_WINDOW: bytes per destination — small values exercise many destinations on small maps)
+  static const size_t window_bytes = [] {
+    const char* e = std::getenv("AMB_DSM_PART_WINDOW");
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? static_cast<size_t>(v) : size_t(48) << 20;
   }();
-  if (direct_binning) {
-    dsm_count_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, n_own, plan, G, counters, hs);
-  } else {
-    // two-level binning (dsm_partition.inc): P1 bins, counts and groups every tile of points by coarse destination
-    PartPlan pp;
-    std::memset(&pp, 0, sizeof(pp));
-    pp.n_own = n_own;
-    pp.n_total = n;
-    // a destination = a band of bucket columns whose final records span ~24 MB at a uniform density (so that the
-    // one or two destinations in flight in P2 stay inside L2); at most kMaxCoarse bands
-    // (development / test knob AMB_DSM_PART_WINDOW: bytes per destination — small values exercise many destinations on
-    //  small maps)
-    static const size_t window_bytes = [] {
-      const char* e = std::getenv("AMB_DSM_PART_WINDOW");
-      const long long v = e ? std::atoll(e) : 0;
-      return v > 0 ? static_cast<size_t>(v) : size_t(24) << 20;
-    }();
-    int S = static_cast<int>(std::min<size_t>((n * sizeof(PointRec) + window_bytes - 1) / window_bytes, kMaxCoarse));
-    S = std::max(1, std::min(S, plan.KC));
-    pp.kj_per = (plan.KC + S - 1) / S;
-    pp.S = (plan.KC + pp.kj_per - 1) / pp.kj_per;
-    pp.n_tiles = static_cast<unsigned int>((n + kPartTile - 1) / kPartTile);
-    pp.n_groups = (pp.n_tiles + kFineTilesPerBlock - 1) / kFineTilesPerBlock;
-    AMB_CUDA(ctx, ctx->records_tmp.reserve(static_cast<size_t>(pp.n_tiles) * kPartTile * sizeof(PointRec)));
-    AMB_CUDA(ctx, ctx->tile_offsets.reserve(static_cast<size_t>(pp.S + 1) * pp.n_tiles * sizeof(unsigned short)));
-    const int part_grid = static_cast<int>(std::min<unsigned int>(pp.n_tiles, kNumSMsB200 * 4u));
-    dsm_partition_kernel<<<part_grid, kPartThreads, 0, s>>>(d_xyz, d_intensities, d_ids, plan, pp, G,
-                                                            ctx->records_tmp.as<PointRec>(),
-                                                            ctx->tile_offsets.as<unsigned short>(), counters, hs);
-    ctx->last_part_plan.assign(reinterpret_cast<const unsigned char*>(&pp),
-                               reinterpret_cast<const unsigned char*>(&pp) + sizeof(pp));
+  int S = static_cast<int>(std::min<size_t>((n * sizeof(PointRec) + window_bytes - 1) / window_bytes, kMaxCoarse));
+  S = std::max(1, std::min(S, plan.KC));
+  pp.kj_per = (plan.KC + S - 1) / S;
+  pp.S = (plan.KC + pp.kj_per - 1) / pp.kj_per;
+  pp.n_tiles = static_cast<unsigned int>((n + kPartTile - 1) / kPartTile);
+  pp.n_groups = (pp.n_tiles + kFineTilesPerBlock - 1) / kFineTilesPerBlock;
+  AMB_CUDA(ctx, ctx->records_tmp.reserve(static_cast<size_t>(pp.n_tiles) * kPartTile * sizeof(PointRec)));
+  AMB_CUDA(ctx, ctx->tile_offsets.reserve(static_cast<size_t>(pp.S + 1) * pp.n_tiles * sizeof(unsigned short)));
+  {
+    PointRec* tmp = ctx->records_tmp.as<PointRec>();
+    unsigned short* offs = ctx->tile_offsets.as<unsigned short>();
+    const unsigned int own_tiles = static_cast<unsigned int>(pp.halo_base / kPartTile);
+    const unsigned int max_grid = kNumSMsB200 * 4u;
+    if (push) {
+      // peer-push exchange (amb_comm.cu): the own points are binned first and their border records stored into the
+      // adjacent ranks' segments on the way; the incoming halos — the tiles after halo_base — follow once both neighbours
+      // have published theirs.  (At least one block even without own points: it publishes the empty lists.)
+      pp.tile_begin = 0;
+      pp.tile_end = own_tiles;
+      dsm_partition_kernel<true><<<std::max(1u, std::min(own_tiles, max_grid)), kPartThreads, 0, s>>>(
+          d_xyz, d_intensities, d_ids, plan, pp, G, tmp, offs, counters, hs, *push);
+      st = halo_wait_launch(ctx, *push);
+      if (st != AMB_OK) return st;
+      pp.tile_begin = own_tiles;
+      pp.tile_end = pp.n_tiles;
+      if (pp.tile_end > pp.tile_begin)
+        dsm_partition_kernel<false><<<std::min(pp.tile_end - pp.tile_begin, max_grid), kPartThreads, 0, s>>>(
+            d_xyz, d_intensities, d_ids, plan, pp, G, tmp, offs, counters, hs, HaloPush());
+      ctx->dsm_launches += 2;
+    } else {
+      pp.tile_begin = 0;
+      pp.tile_end = pp.n_tiles;
+      dsm_partition_kernel<false><<<std::min(pp.n_tiles, max_grid), kPartThreads, 0, s>>>(
+          d_xyz, d_intensities, d_ids, plan, pp, G, tmp, offs, counters, hs, HaloPush());
+    }
   }
   scan_reduce_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(G), n_vec,
                                                  ctx->block_sums.as<unsigned int>());
   scan_spine_kernel<<<1, 1024, 0, s>>>(ctx->block_sums.as<unsigned int>(), scan_blocks);
   scan_apply_kernel<<<scan_blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(G), n_vec,
                                                 ctx->block_sums.as<unsigned int>());
-  if (direct_binning) {
-    dsm_scatter_kernel<<<stream_grid, 256, 0, s>>>(d_xyz, d_intensities, d_ids, n_own, plan, G, rec, hs);
-  } else {
-    PartPlan pp;
-    std::memcpy(&pp, ctx->last_part_plan.data(), sizeof(pp));
-    static const int in_flight = [] {  // development knob
-      const char* e = std::getenv("AMB_DSM_FINE_INFLIGHT");
-      return e ? std::atoi(e) : 2;
-    }();
-    if (in_flight == 4) {
-      dsm_fine_scatter_kernel<4><<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
-          plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
-    } else if (in_flight == 1) {
-      dsm_fine_scatter_kernel<1><<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
-          plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
-    } else {
-      dsm_fine_scatter_kernel<2><<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
-          plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
-    }
-  }
+  dsm_fine_scatter_kernel<<<static_cast<unsigned int>(pp.S) * pp.n_groups, kFineThreads, 0, s>>>(
+      plan, pp, ctx->records_tmp.as<PointRec>(), ctx->tile_offsets.as<unsigned short>(), G, rec);
   // Canonical order inside the buckets: Dsm orders only the buckets its warp-per-cell kernel will read (marked from the
   // cell list after the gather); OrthoFromPcl's adaptive pass may read any bucket, so that mode orders all of them here.
   unsigned char* bucket_flags = ctx->bucket_flags.as<unsigned char>();
