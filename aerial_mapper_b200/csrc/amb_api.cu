@@ -289,8 +289,8 @@ int amb_upload_layer(amb_ctx* ctx, int layer, const float* host_slab) {
   int st = ensure_layer(ctx, layer);
   if (st != AMB_OK) return st;
   wait_layer_copy(ctx, layer);
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->layers[layer], host_slab, ctx->slab_cells() * sizeof(float),
-                                cudaMemcpyHostToDevice, ctx->stream));
+  st = staged_h2d(ctx, ctx->layers[layer], host_slab, ctx->slab_cells() * sizeof(float), ctx->stream);
+  if (st != AMB_OK) return st;
   AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AMB_OK;
 }
@@ -311,10 +311,7 @@ int amb_download_layer(amb_ctx* ctx, int layer, float* host_slab) {
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   int st = ensure_layer(ctx, layer);
   if (st != AMB_OK) return st;
-  AMB_CUDA(ctx, cudaMemcpyAsync(host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float),
-                                cudaMemcpyDeviceToHost, ctx->stream));
-  AMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return AMB_OK;
+  return staged_d2h(ctx, host_slab, ctx->layers[layer], ctx->slab_cells() * sizeof(float), ctx->stream);
 }
 
 int amb_download_layer_async(amb_ctx* ctx, int layer, float* host_slab) {
@@ -400,7 +397,10 @@ int amb_ortho_from_pcl_process(amb_ctx* ctx, const double* xyz, const int32_t* i
   AMB_CUDA(ctx, ctx->points.reserve(n * 3 * sizeof(double)));
   AMB_CUDA(ctx, ctx->intensities.reserve(n * sizeof(int32_t)));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->points.ptr, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    const int sst = staged_h2d(ctx, ctx->points.ptr, xyz, n * 3 * sizeof(double), ctx->stream);
+    if (sst != AMB_OK) return sst;
+  }
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->intensities.ptr, intensities, n * sizeof(int32_t), cudaMemcpyHostToDevice,
                                 ctx->stream));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
@@ -477,10 +477,11 @@ int amb_dsm_process(amb_ctx* ctx, const double* xyz, size_t n, int32_t interpola
   AMB_CUDA(ctx, cudaSetDevice(ctx->device));
   AMB_CUDA(ctx, ctx->points.reserve(n * 3 * sizeof(double)));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_BEGIN], ctx->stream));
-  AMB_CUDA(ctx, cudaMemcpyAsync(ctx->points.ptr, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int st = staged_h2d(ctx, ctx->points.ptr, xyz, n * 3 * sizeof(double), ctx->stream);  // (pageable clouds: host_staging.cu)
+  if (st != AMB_OK) return st;
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], ctx->stream));
   ctx->dsm_had_h2d = true;
-  int st = dsm_run(ctx, ctx->points.as<double>(), nullptr, n, interpolation_radius, center_easting, center_northing);
+  st = dsm_run(ctx, ctx->points.as<double>(), nullptr, n, interpolation_radius, center_easting, center_northing);
   ctx->dsm_timed = (st == AMB_OK);
   if (st != AMB_OK) return st;
   return finish_flags(ctx, CTR_DSM_COINCIDENT, AMB_ERR_COINCIDENT_POINT);

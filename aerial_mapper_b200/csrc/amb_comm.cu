@@ -514,7 +514,8 @@ int amb_dsm_process_sharded(amb_ctx* ctx, const double* xyz, const uint64_t* ids
   AMB_CUDA(ctx, ctx->points.reserve(std::max<size_t>(n_local, 1) * 3 * sizeof(double)));
   AMB_CUDA(ctx, ctx->point_ids.reserve(std::max<size_t>(n_local, 1) * sizeof(uint64_t)));
   if (n_local) {
-    AMB_CUDA(ctx, cudaMemcpyAsync(ctx->points.ptr, xyz, n_local * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int sst = staged_h2d(ctx, ctx->points.ptr, xyz, n_local * 3 * sizeof(double), ctx->stream);
+    if (sst != AMB_OK) return sst;
     AMB_CUDA(ctx, cudaMemcpyAsync(ctx->point_ids.ptr, ids, n_local * sizeof(uint64_t), cudaMemcpyHostToDevice,
                                   ctx->stream));
   }

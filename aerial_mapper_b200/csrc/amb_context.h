@@ -249,6 +249,13 @@ int join_compact_mirrors(amb_ctx* ctx);         // AMB_ERR_CUDA if an expander f
 void wait_compact_layer(amb_ctx* ctx, int layer);  // the expander pool has finished this layer's round
 void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the registered host mirror, if any
 
+// host_staging.cu: copies whose host side may be PAGEABLE memory (staged through pinned slots by a worker pool)
+bool host_memory_is_pageable(const void* p);
+int staged_h2d(amb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s);
+int staged_d2h(amb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);  // synchronous
+int staged_h2d_2d(amb_ctx* ctx, void* dst_dev, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t w,
+                  size_t h, bool pageable, cudaStream_t s);
+
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,
             int32_t interpolation_radius, double center_easting, double center_northing, int mode = 0,

@@ -757,8 +757,10 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     const int w = bbox[4 * f + 2] - r.x0 + 1, h = r.pad_;
     uint8_t* dst = ctx->frames.as<uint8_t>() + off;
     const uint8_t* src = h_images[f] + static_cast<size_t>(r.y0) * row_step + static_cast<size_t>(r.x0) * channels;
-    AMB_CUDA(ctx, cudaMemcpy2DAsync(dst, r.pitch, src, row_step, static_cast<size_t>(w) * channels, h,
-                                    cudaMemcpyHostToDevice, s));
+    // (frames in pageable memory — cv::Mat storage — are packed into pinned slots by the worker pool: host_staging.cu)
+    const int cst = staged_h2d_2d(ctx, dst, static_cast<size_t>(r.pitch), src, row_step, static_cast<size_t>(w) * channels,
+                                  static_cast<size_t>(h), host_memory_is_pageable(h_images[f]), s);
+    if (cst != AMB_OK) return cst;
     ctx->ortho_h2d_bytes += static_cast<int64_t>(w) * channels * h;
     r.ptr = dst;
     off += static_cast<size_t>(r.pitch) * h;

@@ -14,7 +14,10 @@ extern "C" __attribute__((visibility("default"))) int amb_demo_main(int argc, ch
 #define main amb_demo_main
 #endif
 
+#include <chrono>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 
 template <typename T>
@@ -57,11 +60,15 @@ int main(int argc, char** argv) {
   map["elevation_angle"].setConstant(0.0);
   map["num_observations"].setConstant(0);
 
+  // optional third argument: repetitions of the (DSM, orthomosaic) sequence on re-initialised layers, each timed
+  // (tools/shim_bench.py: what the reference's batch demo would get at the benchmark size)
+  const int reps = argc > 3 ? std::atoi(argv[3]) : 1;
+  typedef std::chrono::steady_clock Clock;
+
   dsm::Settings settings_dsm;  // main-ortho-backward-grid.cc:129-133
   settings_dsm.center_easting = 0.0;
   settings_dsm.center_northing = 0.0;
   dsm::Dsm digital_surface_map(settings_dsm, &map);
-  digital_surface_map.process(cloud, &map);
 
   Eigen::Vector4d intr, dist;
   for (int k = 0; k < 4; ++k) {
@@ -82,7 +89,26 @@ int main(int argc, char** argv) {
   ortho::Settings settings_ortho;  // :136-141
   settings_ortho.colored_ortho = hdr[4] == 3;
   ortho::OrthoBackwardGrid mosaic(ncameras, settings_ortho, &map);
-  mosaic.process(T_G_Bs, images, &map);
+
+  for (int rep = 0; rep < reps; ++rep) {
+    if (rep > 0) {  // a fresh map (AerialGridMap::initialize again), outside the timed region
+      map["elevation"].setConstant(NAN);
+      map["observation_index"].setConstant(NAN);
+      map["colored_ortho"].setConstant(NAN);
+      map["ortho"].setConstant(255);
+      map["elevation_angle"].setConstant(0.0);
+    }
+    const Clock::time_point t0 = Clock::now();
+    digital_surface_map.process(cloud, &map);
+    const Clock::time_point t1 = Clock::now();
+    mosaic.process(T_G_Bs, images, &map);
+    const Clock::time_point t2 = Clock::now();
+    if (reps > 1)
+      std::printf("shim_demo rep %d: dsm.process %.2f ms, ortho.process %.2f ms, total %.2f ms\n", rep,
+                  std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                  std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                  std::chrono::duration<double, std::milli>(t2 - t0).count());
+  }
 
   std::ofstream o(argv[2], std::ios::binary);
   const char* names[5] = {"elevation", "elevation_angle", "observation_index", "ortho", "colored_ortho"};
