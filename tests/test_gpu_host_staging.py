@@ -15,6 +15,7 @@ def test_pageable_cloud_layers_and_frames_equal_the_device_path():
     rows, cols, res = 1200, 1100, 0.25          # 5.3 MB layers, staged in both directions
     n = 700_000                                 # 16.8 MB cloud: several chunks would need > 32 MB; one partial chunk here
     xyz = synth.point_cloud(n, rows * res / 2, cols * res / 2, seed=71, holes=3, hole_sides=(2.0, 6.0))
+    n = len(xyz)                                # (the holes removed some)
     camd = synth.scaled_camera(0.5)             # 2000 x 1500 frames (3 MB each); rectangles are packed by the pool
     poses = synth.lawnmower_poses(2, 3, rows * res / 2, cols * res / 2, 150.0, seed=72)
     imgs = [synth.procedural_image(k, camd["width"], camd["height"], 1) for k in range(len(poses))]
@@ -45,6 +46,7 @@ def test_large_pageable_cloud_spans_several_staging_chunks():
     rows, cols, res = 600, 600, 0.5
     n = 3_000_000                               # 72 MB: three 32 MB chunks, the slots are reused
     xyz = synth.point_cloud(n, rows * res / 2, cols * res / 2, seed=73)
+    n = len(xyz)
     gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
     amb.Dsm(amb.DsmSettings(), gm).process(xyz, gm)
     gd = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
