@@ -35,12 +35,16 @@ class Dsm {
     }
     CHECK(map);  // dsm.cc:194
     static_assert(sizeof(Eigen::Vector3d) == 3 * sizeof(double), "AoS double[3] expected");
+    amb_shim::Trace trace("Dsm::process");
     context_.get(*map);
     context_.upload(map, "elevation", AMB_LAYER_ELEVATION);  // cells without neighbours keep their value
+    trace.step("upload (elevation)");
     const double* xyz = &point_cloud[0](0);
     context_.dsmProcess(xyz, point_cloud.size(), settings_.interpolation_radius, settings_.center_easting,
                         settings_.center_northing);
+    trace.step("amb_dsm_process");
     context_.download(map, "elevation", AMB_LAYER_ELEVATION);
+    trace.step("download (elevation)");
   }
 
  private:

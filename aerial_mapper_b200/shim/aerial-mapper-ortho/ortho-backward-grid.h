@@ -75,6 +75,7 @@ class OrthoBackwardGrid {
       CHECK(static_cast<size_t>(images[i].step) == static_cast<size_t>(images[0].step));
       rasters[i] = images[i].data;
     }
+    amb_shim::Trace trace("OrthoBackwardGrid::process");
     context_->get(*map);
     const char* out = settings_.colored_ortho ? "colored_ortho" : "ortho";
     const int out_id = settings_.colored_ortho ? AMB_LAYER_COLORED_ORTHO : AMB_LAYER_ORTHO;
@@ -82,11 +83,14 @@ class OrthoBackwardGrid {
     context_->upload(map, "elevation_angle", AMB_LAYER_ELEVATION_ANGLE);
     context_->upload(map, "observation_index", AMB_LAYER_OBSERVATION_INDEX);
     context_->upload(map, out, out_id);
+    trace.step("uploads (elevation, elevation_angle, observation_index, output layer)");
     context_->orthoProcess(&cam, poses.data(), rasters.data(), n, channels, static_cast<size_t>(images[0].step),
                            settings_.colored_ortho ? 1 : 0);
+    trace.step("amb_ortho_process");
     context_->download(map, "elevation_angle", AMB_LAYER_ELEVATION_ANGLE);
     context_->download(map, "observation_index", AMB_LAYER_OBSERVATION_INDEX);
     context_->download(map, out, out_id);
+    trace.step("downloads (elevation_angle, observation_index, output layer)");
   }
 
  private:

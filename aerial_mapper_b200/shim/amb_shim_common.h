@@ -9,6 +9,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -108,6 +109,34 @@ inline std::shared_ptr<Backend> acquireBackend(const amb_geometry& g) {
   if (k < live.size()) live[k] = b; else live.push_back(b);
   return b;
 }
+
+// AMB_SHIM_TRACE=1: wall-clock trace of the steps inside a process() call on stderr (development aid)
+struct Trace {
+  explicit Trace(const char* what) : on_(enabled()), what_(what) {
+    if (on_) last_ = now();
+  }
+  void step(const char* name) {
+    if (!on_) return;
+    const double t = now();
+    std::fprintf(stderr, "[amb shim] %s: %s %.2f ms\n", what_, name, (t - last_) * 1e3);
+    last_ = t;
+  }
+  static bool enabled() {
+    static const bool on = [] {
+      const char* e = std::getenv("AMB_SHIM_TRACE");
+      return e && e[0] == '1';
+    }();
+    return on;
+  }
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return static_cast<double>(ts.tv_sec) + 1e-9 * static_cast<double>(ts.tv_nsec);
+  }
+  bool on_;
+  const char* what_;
+  double last_;
+};
 
 class Context {
  public:

@@ -50,7 +50,8 @@ for label, env in (("host layers authoritative (default)", {}),
                    ("AMB_SHIM_RESIDENT_LAYERS=1", {"AMB_SHIM_RESIDENT_LAYERS": "1"}),
                    ("driver staging (AMB_STAGING_OFF=1), default layers", {"AMB_STAGING_OFF": "1"})):
     r = subprocess.run([exe, scen, os.path.join(tmp, "layers.bin"), str(reps)], capture_output=True, text=True,
-                       env=dict(os.environ, **env))
+                       env=dict(os.environ, AMB_SHIM_TRACE="1", **env))
+    print("\n".join(r.stderr.splitlines()[-9:]), flush=True)   # the last repetition's step trace
     lines = [l for l in r.stdout.splitlines() if l.startswith("shim_demo rep")]
     if r.returncode != 0 or not lines:
         print(json.dumps({"config": label, "error": (r.stdout + r.stderr)[-500:]}))
