@@ -253,8 +253,13 @@ void release_compact_mirrors(amb_ctx* ctx);     // enqueue_layer_download to the
 bool host_memory_is_pageable(const void* p);
 int staged_h2d(amb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s);
 int staged_d2h(amb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);  // synchronous
-int staged_h2d_2d(amb_ctx* ctx, void* dst_dev, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t w,
-                  size_t h, bool pageable, cudaStream_t s);
+struct StagedRect {
+  unsigned char* dst;        // device
+  size_t dst_pitch;
+  const unsigned char* src;  // host
+  size_t src_pitch, w, h;    // bytes per row, rows
+};
+int staged_h2d_rects(amb_ctx* ctx, const StagedRect* rects, size_t n, cudaStream_t s);
 
 // Implemented in dsm_kernels.cu / ortho_kernels.cu
 int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, size_t n,

@@ -751,6 +751,8 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
   AMB_CUDA(ctx, ctx->frames.reserve(total + 256));
   AMB_CUDA(ctx, ctx->frame_rects.reserve(n * sizeof(FrameRect)));
   size_t off = 0;
+  std::vector<StagedRect> copies;
+  copies.reserve(n);
   for (size_t f = 0; f < n; ++f) {
     FrameRect& r = rects[f];
     if (bbox[4 * f + 2] < 0) continue;
@@ -758,13 +760,16 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     uint8_t* dst = ctx->frames.as<uint8_t>() + off;
     const uint8_t* src = h_images[f] + static_cast<size_t>(r.y0) * row_step + static_cast<size_t>(r.x0) * channels;
     // (frames in pageable memory — cv::Mat storage — are packed into pinned slots by the worker pool: host_staging.cu)
-    const int cst = staged_h2d_2d(ctx, dst, static_cast<size_t>(r.pitch), src, row_step, static_cast<size_t>(w) * channels,
-                                  static_cast<size_t>(h), host_memory_is_pageable(h_images[f]), s);
-    if (cst != AMB_OK) return cst;
+    copies.push_back(StagedRect{dst, static_cast<size_t>(r.pitch), src, row_step, static_cast<size_t>(w) * channels,
+                                static_cast<size_t>(h)});
     ctx->ortho_h2d_bytes += static_cast<int64_t>(w) * channels * h;
     r.ptr = dst;
     off += static_cast<size_t>(r.pitch) * h;
     r.pad_ = 0;
+  }
+  {
+    const int cst = staged_h2d_rects(ctx, copies.data(), copies.size(), s);
+    if (cst != AMB_OK) return cst;
   }
   AMB_CUDA(ctx, cudaMemcpyAsync(ctx->frame_rects.ptr, rects, n * sizeof(FrameRect), cudaMemcpyHostToDevice, s));
   AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_ORTHO_COPY_END], s));
