@@ -670,6 +670,8 @@ int dsm_run(amb_ctx* ctx, const double* d_xyz, const unsigned long long* d_ids, 
           d_xyz, d_intensities, d_ids, plan, pp, G, tmp, offs, counters, hs, *push);
       st = halo_wait_launch(ctx, *push);
       if (st != AMB_OK) return st;
+      // timings: the "halo" interval of a peer-push step ends here (own points binned + pushed, neighbours' halos arrived)
+      AMB_CUDA(ctx, cudaEventRecord(ctx->events[EV_DSM_H2D_END], s));
       pp.tile_begin = own_tiles;
       pp.tile_end = pp.n_tiles;
       if (pp.tile_end > pp.tile_begin)

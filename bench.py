@@ -407,9 +407,15 @@ def run_ours(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         enqueue_step(gm, dsm, ortho, sharded)
+    enqueue_ms = (time.perf_counter() - t0) * 1e3 / args.steps   # host time to enqueue a step (host-bound if ~ ms_per_step)
     gm.sync()          # one synchronisation for the K steps (also reports any deferred reference CHECK / halo overflow)
     torch.cuda.synchronize()
     my_ms = (time.perf_counter() - t0) * 1e3
+    # stage times of the LAST step of the back-to-back region (the library's own CUDA events): what a stage costs in the
+    # pipeline, waits for neighbours included — the individually synchronised steps below add process launch skew at N>1
+    tm_last = gm.timings()
+    last_step = [tm_last["dsm_h2d_ms"], tm_last["dsm_bin_ms"], tm_last["dsm_gather_ms"], tm_last["dsm_fill_ms"],
+                 tm_last["ortho_kernel_ms"]]
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([my_ms], dtype=torch.float64, device=device)
@@ -440,9 +446,13 @@ def run_ours(args):
     csum = torch.tensor([layer_bits_sum(torch, gm, result_names, c0, c1) % (1 << 62)], dtype=torch.int64, device=device)
     smax = torch.tensor([stage_ms[k] for k in ("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho")],
                         dtype=torch.float64, device=device)
+    lmax = torch.tensor(last_step, dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(csum, op=dist.ReduceOp.SUM)
         dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lmax, op=dist.ReduceOp.MAX)
+    stage_ms_in_flight = dict(zip(("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho_last_launch"),
+                                  [float(x) for x in lmax.tolist()]))
     checksum = int(csum.item()) % (1 << 62)
     stage_ms = dict(zip(("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho"), [float(x) for x in smax.tolist()]))
 
@@ -535,7 +545,8 @@ def run_ours(args):
                       "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W * channels) / 1e9),
                       "timed_region": "K steps enqueued back to back, one synchronisation at the end"},
            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline,
-           "checksum": checksum, "rank_ms_per_step": rank_ms_per_step, "dsm_cells_exact_path": int(cells_exact)}
+           "checksum": checksum, "rank_ms_per_step": rank_ms_per_step, "dsm_cells_exact_path": int(cells_exact),
+           "host_enqueue_ms_per_step": enqueue_ms, "stage_ms_last_timed_step": stage_ms_in_flight}
     if verify is not None:
         out["sharded_equals_undivided"] = verify
     if incremental_ok is not None:
