@@ -453,6 +453,11 @@ def run_ours(args):
         dist.all_reduce(lmax, op=dist.ReduceOp.MAX)
     stage_ms_in_flight = dict(zip(("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho_last_launch"),
                                   [float(x) for x in lmax.tolist()]))
+    if world > 1:   # per rank too: who waits for whom (dsm_halo of a peer-push step = own binning + push + WAIT for the neighbours)
+        mine_t = torch.tensor(last_step, dtype=torch.float64, device=device)
+        every = [mine_t.clone() for _ in range(world)]
+        dist.all_gather(every, mine_t)
+        stage_ms_in_flight["per_rank"] = [[round(float(v), 4) for v in t_.tolist()] for t_ in every]
     checksum = int(csum.item()) % (1 << 62)
     stage_ms = dict(zip(("dsm_halo", "dsm_bin", "dsm_gather", "dsm_fill", "ortho"), [float(x) for x in smax.tolist()]))
 
