@@ -1,7 +1,8 @@
 """Basic-block breakdown of one kernel of an .ncu-rep (SASS page): instructions executed, share of samples, lanes.
-    python tools/ncu_blocks.py gpurun_out/x.ncu-rep [min_share_pct]"""
+    python tools/ncu_blocks.py gpurun_out/x.ncu-rep [min_share_pct] [kernel-name regex]"""
 import csv, subprocess, sys
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.4
 hdr = rows[1]; data = rows[2:]
