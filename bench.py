@@ -515,6 +515,17 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": int(alg), "kernel_ms": stage_ms["dsm_gather"],
                      "issue_active_pct": cap.get("issue_active_pct"), "fp64_pipe_active_pct": cap.get("fp64_pipe_active_pct"),
                      "limiter": cap.get("limiter", "instruction issue (see profiles/), not HBM")})
+        # the binning stage (dsm_partition_kernel -> scan -> dsm_fine_scatter_kernel): the HBM-bound part of the path.
+        # Algorithmic bytes of the two-level scheme: 24 B read + 32 B written per point (P1), 32 + 32 B per point (P2).
+        alg_bin = (24 + 32 + 32 + 32) * n_rank_points
+        ach_bin = alg_bin / (stage_ms["dsm_bin"] * 1e-3) / 1e9
+        cap = traffic_db.get("dsm_binning", {})
+        roof.append({"kernel": "dsm_partition_kernel + scan + dsm_fine_scatter_kernel (binning stage)", "bound": "hbm",
+                     "achieved": ach_bin, "peak": peak, "unit": "GB/s", "frac": ach_bin / peak,
+                     "traffic": cap.get("traffic_bytes_per_launch"), "algorithmic_bytes_per_launch": int(alg_bin),
+                     "kernel_ms": stage_ms["dsm_bin"], "issue_active_pct": cap.get("issue_active_pct"),
+                     "fp64_pipe_active_pct": cap.get("fp64_pipe_active_pct"),
+                     "limiter": cap.get("limiter", "HBM (see profiles/)")})
     if do_ortho:
         launches = (n_frames // batch) if batch else 1
         alg = (ORTHO_BYTES_PER_CELL + channels) * stripe_cells
