@@ -216,7 +216,7 @@ void amb_destroy(amb_ctx* ctx) {
   DeviceBuffer* bufs[] = {&ctx->points,  &ctx->point_ids, &ctx->intensities, &ctx->records, &ctx->records_tmp, &ctx->tile_offsets, &ctx->point_order, &ctx->bucket_flags,
                             &ctx->bin_starts, &ctx->block_sums, &ctx->empty_cells,
                           &ctx->counters, &ctx->dbg_count, &ctx->dbg_level,  &ctx->frames,     &ctx->frame_table,
-                          &ctx->frame_cull, &ctx->ortho_tile_lists, &ctx->frame_rects, &ctx->ortho_pix, &ctx->ortho_bbox};
+                          &ctx->frame_cull, &ctx->frame_rects, &ctx->ortho_pix, &ctx->ortho_bbox};
   for (DeviceBuffer* b : bufs) b->release();
   for (int k = 0; k < EV_COUNT; ++k)
     if (ctx->events[k]) cudaEventDestroy(ctx->events[k]);

@@ -208,7 +208,6 @@ struct amb_ctx {
   // Ortho scratch
   amb::DeviceBuffer frames;       // device copies of the caller's frames (host entry point)
   amb::DeviceBuffer frame_table;  // per-frame device image pointers
-  amb::DeviceBuffer ortho_tile_lists;  // split orthomosaic kernels: per tile [count, candidate frames...] (uint16)
   amb::DeviceBuffer frame_cull;   // per-frame camera centre + R_C_G rows (tile cull test)
   amb::DeviceBuffer frame_rects;  // host-frame path: per-frame uploaded sub-rectangle
   amb::DeviceBuffer ortho_pix;    // host-frame path: winner pixel per cell

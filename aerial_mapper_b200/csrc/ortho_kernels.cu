@@ -23,7 +23,6 @@ namespace amb {
 namespace {
 
 constexpr int kMaxFramesPerLaunch = 512;
-constexpr int kTileListStride = kMaxFramesPerLaunch + 1;  // split kernels: per tile [count, frames...] (uint16)
 #ifndef AMB_OTI
 #define AMB_OTI 32
 #endif
@@ -32,9 +31,6 @@ static_assert(OTI % 32 == 0, "a warp covers 32 consecutive rows");
 constexpr int OTJ = 32;  // tile extent along j
 #ifndef AMB_OSTRIP
 #define AMB_OSTRIP 4
-#endif
-#ifndef AMB_OBPS_CULL
-#define AMB_OBPS_CULL 6   // resident blocks/SM of the cull-only kernel (<= 40 registers)
 #endif
 #ifndef AMB_OBPS
 #define AMB_OBPS 4   // measured at joint_10k: 3 blocks/SM (80 registers) 3.04 ms, 4 blocks/SM (64 registers) 2.86 ms
@@ -68,7 +64,6 @@ struct OrthoArgs {
   const uint8_t* const* images;   // device array: frame -> device raster
   const double* cull_data;        // device array [n_frames][12]: camera centre, R_C_G rows (map frame)
   unsigned int* error_flag;
-  unsigned short* tile_lists;     // split kernels (AMB_ORTHO_PHASE 1 / 2): per tile [count, candidate frames...]
   unsigned int* pix;              // SELECT mode: per cell (py << 16 | px) of the winner, untouched if not updated
   int* bbox;                      // SELECT mode: per frame [xmin, ymin, xmax, ymax] of the winners' pixels
   size_t row_step;
@@ -273,20 +268,8 @@ __device__ __forceinline__ double observation_angle(double xc, double yc, double
 #define AMB_ORTHO_DOM 1
 #define AMB_ORTHO_KERNEL_NAME ortho_kernel_dom
 #include "ortho_kernel_body.inc"
-#undef AMB_ORTHO_KERNEL_NAME
-// the same kernel split in two (see AMB_ORTHO_PHASE in the body): cull lists first, selection second
-#undef AMB_ORTHO_PHASE
-#define AMB_ORTHO_PHASE 1
-#define AMB_ORTHO_KERNEL_NAME ortho_cull_kernel_dom
-#include "ortho_kernel_body.inc"
-#undef AMB_ORTHO_KERNEL_NAME
-#undef AMB_ORTHO_PHASE
-#define AMB_ORTHO_PHASE 2
-#define AMB_ORTHO_KERNEL_NAME ortho_select_kernel_dom
-#include "ortho_kernel_body.inc"
-#undef AMB_ORTHO_KERNEL_NAME
-#undef AMB_ORTHO_PHASE
 #undef AMB_ORTHO_DOM
+#undef AMB_ORTHO_KERNEL_NAME
 
 // Bounding boxes device -> HOST-MAPPED pinned memory with plain stores: the read-back must not queue behind the
 // result layers that are streaming to the host on the device->host copy engine.
@@ -674,18 +657,6 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.dom_sin_margin = std::sin(a.dom_margin);
   }
   const int tiles_i = (a.rows + OTI - 1) / OTI, tiles_j = (a.cols_slab + OTJ - 1) / OTJ;
-  // split kernels (cull lists, then selection): development switch AMB_ORTHO_SPLIT=0|1
-  static const bool split_default = [] {
-    const char* e = std::getenv("AMB_ORTHO_SPLIT");
-    return e ? e[0] == '1' : false;
-  }();
-  const bool split = dominance && split_default;
-  a.tile_lists = nullptr;
-  if (split) {
-    AMB_CUDA(ctx, ctx->ortho_tile_lists.reserve(static_cast<size_t>(tiles_i) * tiles_j * kTileListStride *
-                                                sizeof(unsigned short)));
-    a.tile_lists = ctx->ortho_tile_lists.as<unsigned short>();
-  }
   ctx->ortho_launches = 0;
   for (size_t f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {  // ascending chunks keep the frame order
     const size_t nf = std::min<size_t>(kMaxFramesPerLaunch, n - f0);
@@ -701,30 +672,7 @@ int ortho_run(amb_ctx* ctx, const amb_camera* camera, const double* T_G_B, const
     a.cull_data = ctx->frame_cull.as<double>() + 12 * f0;
     a.exact_data = ctx->frame_cull.as<double>() + 12 * n + 8 * f0;
     const int grid = tiles_i * tiles_j;
-    if (dominance && split) {
-      // cull lists first (light kernel, higher occupancy), selection second
-      ortho_cull_kernel_dom<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
-      ctx->ortho_launches += 1;
-      if (select_only) {
-        if (a.dist_type == AMB_DIST_RADTAN) {
-          ortho_select_kernel_dom<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
-        } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
-          ortho_select_kernel_dom<AMB_DIST_EQUIDISTANT, true><<<grid, kOrthoThreads, 0, s>>>(a);
-        } else if (a.dist_type == AMB_DIST_FOV) {
-          ortho_select_kernel_dom<AMB_DIST_FOV, true><<<grid, kOrthoThreads, 0, s>>>(a);
-        } else {
-          ortho_select_kernel_dom<AMB_DIST_NONE, true><<<grid, kOrthoThreads, 0, s>>>(a);
-        }
-      } else if (a.dist_type == AMB_DIST_RADTAN) {
-        ortho_select_kernel_dom<AMB_DIST_RADTAN, false><<<grid, kOrthoThreads, 0, s>>>(a);
-      } else if (a.dist_type == AMB_DIST_EQUIDISTANT) {
-        ortho_select_kernel_dom<AMB_DIST_EQUIDISTANT, false><<<grid, kOrthoThreads, 0, s>>>(a);
-      } else if (a.dist_type == AMB_DIST_FOV) {
-        ortho_select_kernel_dom<AMB_DIST_FOV, false><<<grid, kOrthoThreads, 0, s>>>(a);
-      } else {
-        ortho_select_kernel_dom<AMB_DIST_NONE, false><<<grid, kOrthoThreads, 0, s>>>(a);
-      }
-    } else if (dominance) {
+    if (dominance) {
       if (select_only) {
         if (a.dist_type == AMB_DIST_RADTAN) {
           ortho_kernel_dom<AMB_DIST_RADTAN, true><<<grid, kOrthoThreads, 0, s>>>(a);
