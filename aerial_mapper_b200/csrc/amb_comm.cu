@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256) dsm_halo_records_kernel(const double* __r
 // after it has finished reading the earlier one (stream order) — so a segment is never overwritten while it is read.
 //
 // Lane 0 / 1: wait until the header of the segment filled by rank - 1 / rank + 1 carries this step's stamp.
-// Bounded (about two seconds of polling): a neighbour that never arrives raises the sticky halo flag instead of hanging
-// the GPU.
+// Bounded (about twenty seconds of polling — far beyond any legitimate skew between ranks): a neighbour that never arrives
+// raises the sticky halo flag instead of hanging the GPU.
 __global__ void halo_wait_kernel(const unsigned char* seg_prev, const unsigned char* seg_next, unsigned int stamp,
                                  unsigned int* counters) {
   const unsigned char* seg = threadIdx.x == 0 ? seg_prev : seg_next;
@@ -164,7 +164,7 @@ __global__ void halo_wait_kernel(const unsigned char* seg_prev, const unsigned c
   for (;;) {
     const unsigned long long h = load_acquire_sys(seg);
     if (static_cast<unsigned int>(h >> 32) == stamp) return;
-    if (clock64() - t0 > 4000000000ll) {
+    if (clock64() - t0 > 40000000000ll) {
       atomicExch(&counters[CTR_HALO_OVERFLOW], 1u);
       return;
     }
@@ -215,7 +215,15 @@ static int peer_halo_setup(amb_ctx* ctx, uint32_t side_capacity) {
   HaloPeer& hp = ctx->halo_peer;
   cudaStream_t s = ctx->stream;
   const int nranks = ctx->comm_size, rank = ctx->comm_rank;
-  AMB_CUDA(ctx, cudaStreamSynchronize(s));  // nobody may still be reading / writing the segments that are replaced
+  AMB_CUDA(ctx, cudaStreamSynchronize(s));  // this rank no longer reads its segments nor writes its neighbours'
+  // A neighbour may still be pushing into this rank's OLD segments (it reaches this collective later): on a re-setup
+  // (larger capacity) they are retired, not freed — amb_comm_destroy frees them.
+  if (hp.recv) {
+    hp.retired.push_back(hp.recv);
+    hp.retired.push_back(reinterpret_cast<unsigned char*>(hp.counters));
+    hp.recv = nullptr;
+    hp.counters = nullptr;
+  }
   peer_halo_release(ctx);
   hp.tried = true;
   const size_t side_bytes = 32 * (static_cast<size_t>(side_capacity) + 1);
@@ -355,6 +363,8 @@ int amb_comm_destroy(amb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     peer_halo_release(ctx);
+    for (unsigned char* p : ctx->halo_peer.retired) cudaFree(p);
+    ctx->halo_peer.retired.clear();
     nccl().comm_destroy(static_cast<nccl_comm_t>(ctx->nccl_comm));
   }
   ctx->nccl_comm = nullptr;

@@ -137,6 +137,7 @@ struct HaloPeer {
   bool prev_ipc = false, next_ipc = false;
   uint32_t side_capacity = 0, tried_capacity = 0;
   uint64_t step = 0;
+  std::vector<unsigned char*> retired;   // segments replaced by a larger re-setup: freed when the communicator is left
 };
 
 struct HaloSource {

@@ -184,6 +184,9 @@ int staged_h2d(amb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, 
     parallel_copy(sl->buf[slot], static_cast<const unsigned char*>(src_host) + off, len);
     AMB_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(dst_dev) + off, sl->buf[slot], len, cudaMemcpyHostToDevice, s));
     AMB_CUDA(ctx, cudaEventRecord(sl->ev[slot], s));
+#ifdef AMB_CUDA_EMU  // tests/emu only: the staged path ran (tests/test_emulated_kernels.py)
+    emu::note("staged_h2d_chunks", 1);
+#endif
     off += len;
   }
   return AMB_OK;
@@ -215,6 +218,9 @@ int staged_d2h(amb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, 
     const size_t off = k * kChunk, len = std::min(kChunk, bytes - off);
     AMB_CUDA(ctx, cudaEventSynchronize(sl->ev[k % kSlots]));
     parallel_copy(static_cast<unsigned char*>(dst_host) + off, sl->buf[k % kSlots], len);
+#ifdef AMB_CUDA_EMU
+    emu::note("staged_d2h_chunks", 1);
+#endif
   }
   return AMB_OK;
 }
@@ -296,6 +302,9 @@ int staged_h2d_rects(amb_ctx* ctx, const StagedRect* rects, size_t n, cudaStream
     });
     AMB_CUDA(ctx, cudaMemcpyAsync(dev_begin, stage, used, cudaMemcpyHostToDevice, s));
     AMB_CUDA(ctx, cudaEventRecord(sl->ev[slot], s));
+#ifdef AMB_CUDA_EMU
+    emu::note("staged_rect_slots", 1);
+#endif
   }
   return AMB_OK;
 }

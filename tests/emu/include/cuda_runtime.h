@@ -21,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 
 #define AMB_CUDA_EMU 1
 
@@ -86,8 +88,36 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefau
        cudaHostAllocPortable = 1 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
 struct cudaPointerAttributes { cudaMemoryType type; };
-// every host pointer counts as pinned on the emulation: the staged (pageable) copy path of host_staging.cu stays off
-inline int cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeHost; return 0; }
+namespace emu {
+// blocks handed out by cudaHostAlloc (for AMB_EMU_PAGEABLE, below)
+inline std::map<uintptr_t, size_t>& pinned_blocks() {
+  static std::map<uintptr_t, size_t> m;
+  return m;
+}
+inline std::mutex& pinned_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+inline bool is_pinned(const void* p) {
+  std::lock_guard<std::mutex> g(pinned_mutex());
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  std::map<uintptr_t, size_t>::const_iterator it = pinned_blocks().upper_bound(a);
+  if (it == pinned_blocks().begin()) return false;
+  --it;
+  return a < it->first + it->second;
+}
+}  // namespace emu
+// every host pointer counts as pinned on the emulation, so the staged (pageable) copy path of host_staging.cu stays off —
+// unless AMB_EMU_PAGEABLE=1: then every pointer that did not come from cudaHostAlloc / cudaMallocHost counts as pageable
+// and the chunking / slot reuse / rectangle packing logic of that file runs on the CPU (tests/test_emulated_kernels.py)
+inline int cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  static const bool pageable = [] {
+    const char* e = std::getenv("AMB_EMU_PAGEABLE");
+    return e && e[0] == '1';
+  }();
+  a->type = (pageable && !emu::is_pinned(p)) ? cudaMemoryTypeUnregistered : cudaMemoryTypeHost;
+  return 0;
+}
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 
@@ -130,10 +160,18 @@ inline cudaError_t cudaFree(void* p) {
 template <typename T>
 inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) {
   *p = static_cast<T*>(std::malloc(bytes ? bytes : 1));
-  if (*p) std::memset(*p, 0xA5, bytes ? bytes : 1);
+  if (*p) {
+    std::memset(*p, 0xA5, bytes ? bytes : 1);
+    std::lock_guard<std::mutex> g(emu::pinned_mutex());
+    emu::pinned_blocks()[reinterpret_cast<uintptr_t>(*p)] = bytes ? bytes : 1;
+  }
   return *p ? cudaSuccess : cudaErrorInvalidValue;
 }
 inline cudaError_t cudaFreeHost(void* p) {
+  {
+    std::lock_guard<std::mutex> g(emu::pinned_mutex());
+    emu::pinned_blocks().erase(reinterpret_cast<uintptr_t>(p));
+  }
   std::free(p);
   return cudaSuccess;
 }

@@ -110,3 +110,46 @@ def test_the_product_never_reaches_for_the_emulated_library():
                 assert "libamb_emu" not in text and "tests/emu/" .replace(" ", "") not in text.replace("tests/emu (", "").replace("tests/emu only", ""), f
     assert "AMB_TEST_EMU" not in open(os.path.join(ROOT, "bench.py")).read()
     assert "emu" not in open(os.path.join(ROOT, "__graft_entry__.py")).read()
+
+
+def test_pageable_staging_logic_on_the_emulated_runtime(tmp_path):
+    # csrc/host_staging.cu (worker pool, pinned slots, chunking, slot-wise packing of the frame rectangles) with
+    # AMB_EMU_PAGEABLE=1: every caller buffer counts as pageable, so the staged paths run — same layers as the direct path
+    import json
+    code = r'''
+import os, sys, json, ctypes as C
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import conftest
+import numpy as np
+import aerial_mapper_b200 as amb
+from aerial_mapper_b200 import synth, _lib
+rows, cols, res = 1100, 1000, 0.25            # 4.4 MB layers, 4.8 MB cloud: above the 4 MB staging threshold
+xyz = synth.point_cloud(200000, rows * res / 2, cols * res / 2, seed=71, holes=3, hole_sides=(2.0, 6.0))
+camd = synth.scaled_camera(0.25)
+poses = synth.lawnmower_poses(2, 3, rows * res / 2, cols * res / 2, 150.0, seed=72)
+imgs = [synth.procedural_image(k, camd["width"], camd["height"], 1) for k in range(len(poses))]
+gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+amb.Dsm(amb.DsmSettings(), gm).process(xyz, gm)
+amb.OrthoBackwardGrid(amb.NCamera(**camd), amb.OrthoSettings(), gm).process(poses, imgs, gm)
+np.save(sys.argv[1], np.stack([gm[k] for k in ("elevation", "elevation_angle", "observation_index", "ortho")]))
+out = {}
+for key in ("staged_h2d_chunks", "staged_d2h_chunks", "staged_rect_slots"):
+    s, n = C.c_longlong(0), C.c_longlong(0)
+    _lib._lib.amb_emu_counter(key.encode(), C.byref(s), C.byref(n))
+    out[key] = int(n.value)
+print(json.dumps(out))
+''' % (ROOT, ROOT)
+    script = tmp_path / "staged.py"
+    script.write_text(code)
+    import numpy as np
+    results = {}
+    for pageable in ("1", "0"):
+        env = dict(os.environ, AMB_TEST_EMU="1", AMB_EMU_PAGEABLE=pageable)
+        out = tmp_path / ("layers_%s.npy" % pageable)
+        r = subprocess.run([sys.executable, str(script), str(out)], cwd=ROOT, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+        results[pageable] = (np.load(out), json.loads(r.stdout.strip().splitlines()[-1]))
+    staged, direct = results["1"], results["0"]
+    assert staged[1]["staged_h2d_chunks"] >= 3 and staged[1]["staged_d2h_chunks"] >= 3 and staged[1]["staged_rect_slots"] >= 1
+    assert direct[1] == {"staged_h2d_chunks": 0, "staged_d2h_chunks": 0, "staged_rect_slots": 0}
+    assert np.array_equal(staged[0].view(np.uint32), direct[0].view(np.uint32))
