@@ -546,20 +546,20 @@ def run_ours(args):
            "dtype": ("f32 (DSM weights/sums; neighbour decisions exact vs f64) + f64 (orthomosaic)" if lib_prec == "f32"
                      else "f64") if do_dsm else "f64",
            "data": "synthetic",
-           "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res), "points": int(n_points),
-                      "frames": ("%dx %dx%d %s" % (n_frames, W, H, "BGR" if colored else "gray")) if do_ortho else "none",
-                      "frame_batches": (n_frames // batch) if batch else (1 if do_ortho else 0),
-                      "interpolation_radius": 1, "dsm_precision": lib_prec if do_dsm else None,
-                      "sharding": ("column stripes x%d; cloud sharded by stripe; border halos exchanged inside the library on "
-                                   "its own stream (%s); layers stay sharded"
-                                   % (world, {0: "not a DSM workload", 1: "one ncclAllGather",
-                                              2: "ncclSend/ncclRecv with the two adjacent ranks",
-                                              4: "peer push: the compaction kernel stores into the two adjacent ranks' "
-                                                 "segments over NVLink peer memory, no collective call in the step"}
-                                   [int(amb.lib().amb_comm_last_exchange(ctx))]))
-                      if world > 1 else "single GPU",
-                      "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W * channels) / 1e9),
-                      "timed_region": "K steps enqueued back to back, one synchronisation at the end"},
+           # `config` names the workload and is IDENTICAL in both arms (shared_config); what is specific to this arm's run
+           # is in `run`
+           "config": shared_config(args.workload, rows, cols, res, wl["n_points"], n_frames, W, H, colored, do_ortho, batch,
+                                   channels),
+           "run": {"dsm_precision": lib_prec if do_dsm else None, "points_in_the_cloud": int(n_points),
+                   "sharding": ("column stripes x%d; cloud sharded by stripe; border halos exchanged inside the library on "
+                                "its own stream (%s); layers stay sharded"
+                                % (world, {0: "not a DSM workload", 1: "one ncclAllGather",
+                                           2: "ncclSend/ncclRecv with the two adjacent ranks",
+                                           4: "peer push: the compaction kernel stores into the two adjacent ranks' "
+                                              "segments over NVLink peer memory, no collective call in the step"}
+                                [int(amb.lib().amb_comm_last_exchange(ctx))]))
+                   if world > 1 else "single GPU",
+                   "timed_region": "K steps enqueued back to back, one synchronisation at the end"},
            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline,
            "checksum": checksum, "rank_ms_per_step": rank_ms_per_step, "dsm_cells_exact_path": int(cells_exact),
            "host_enqueue_ms_per_step": enqueue_ms, "stage_ms_last_timed_step": stage_ms_in_flight}
@@ -773,11 +773,17 @@ def cpu_reference(args, steps, warmup):
     base = {"value": value, "unit": "cells/s", "cores": threads, "kind": kind, "sample": sample, "extrapolated": True,
             "sample_fraction": sample_cells / float(rows * cols)}
     return {"cpu_baseline": base, "ms_per_step": t_step * 1e3, "value": value,
-            "config": {"workload": args.workload, "grid": "%dx%d@%gm" % (rows, cols, res),
-                       "points": int(wl["n_points"]),
-                       "frames": ("%dx %dx%d %s" % (n_frames, camd["width"], camd["height"], "BGR" if colored else "gray"))
-                       if do_ortho else "none",
-                       "interpolation_radius": 1}}
+            "config": shared_config(args.workload, rows, cols, res, wl["n_points"], n_frames, camd["width"], camd["height"],
+                                    colored, do_ortho, batch, 3 if colored else 1)}
+
+
+def shared_config(workload, rows, cols, res, n_points, n_frames, W, H, colored, do_ortho, batch, channels):
+    """The workload as both arms name it (same keys, same values: the driver compares the two lines' `config`)."""
+    return {"workload": workload, "grid": "%dx%d@%gm" % (rows, cols, res), "points": int(n_points),
+            "frames": ("%dx %dx%d %s" % (n_frames, W, H, "BGR" if colored else "gray")) if do_ortho else "none",
+            "frame_batches": (n_frames // batch) if batch else (1 if do_ortho else 0),
+            "interpolation_radius": 1,
+            "l2": "inputs (%.1f GB) larger than L2" % ((n_points * 24 + n_frames * H * W * channels) / 1e9)}
 
 
 def run_reference(args):

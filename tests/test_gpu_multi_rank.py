@@ -47,4 +47,4 @@ def test_every_exchange_mode_equals_the_undivided_map(workload, modes):
         assert two.get("sharded_equals_undivided") is True, (env, two)
         assert two["checksum"] == one["checksum"], (env, two["checksum"], one["checksum"])
         expect = "peer push" if env is PEER else ("ncclSend/ncclRecv" if env is SENDRECV else "ncclAllGather")
-        assert expect in two["config"]["sharding"], two["config"]["sharding"]
+        assert expect in two["run"]["sharding"], two["run"]["sharding"]
