@@ -185,3 +185,93 @@ def test_shim_resident_layers_and_repetitions_give_the_same_layers(tmp_path):
         for k in range(4):   # elevation, elevation_angle, observation_index, ortho
             assert np.array_equal(got[label][0][k].view(np.uint32), got["default"][0][k].view(np.uint32)), (label, k)
     assert "[amb shim] Dsm::process: amb_dsm_process" in got["default"][1]   # the AMB_SHIM_TRACE step trace
+
+
+def test_peer_push_producer_on_local_stand_in_segments(tmp_path):
+    # The producer side of the peer-push halo exchange — dsm_partition_kernel<PUSH> + halo_publish (per-tile slot
+    # reservation, both sides at once, header {count | stamp << 32}) — needs other ranks' memory on hardware.  The
+    # emulated library's test hook amb_emu_self_push (tests/emu/emu_test_hooks.cc) points the two "neighbour segments" at
+    # local buffers: the pushed records must be exactly the stripe's border points, and the stripe's elevation must equal
+    # the one of the same points binned without a push.
+    import json
+    code = r'''
+import os, sys, json, ctypes as C
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import conftest
+import numpy as np
+import aerial_mapper_b200 as amb
+from aerial_mapper_b200 import synth, sharding, _lib
+L = _lib._lib
+L.amb_emu_self_push.restype = C.c_int
+L.amb_emu_self_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_double, C.c_double, C.c_uint,
+                                C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
+rows, cols, res = 160, 224, 0.5
+c0, c1 = 64, 160                      # a middle stripe: both neighbours exist; 96 columns >= reach (35 cells)
+center_e = 3.25                       # dsm::Settings::center_easting: the border test uses y - center_easting
+xyz_all = synth.point_cloud(90000, rows * res / 2, cols * res / 2, seed=81)
+xyz_all[:, 1] += center_e
+ids_all = np.arange(len(xyz_all), dtype=np.uint64) * 7 + 3          # global ids: unique, not the array positions
+out = {}
+def stripe_map():
+    gm = amb.AerialGridMap(amb.GridMapSettings(0, 0, rows * res, cols * res, res)).getMutable()
+    gm.to_device(0, col_range=(c0, c1))
+    return gm
+gm = stripe_map()
+y_lo, y_hi = sharding.stripe_y_interval(gm.geometry, c0, c1)
+reach = L.amb_dsm_halo_reach(C.byref(gm.geometry), 1)
+ys = xyz_all[:, 1] - center_e
+own = (ys > y_lo) & (ys <= y_hi)
+xyz = np.ascontiguousarray(xyz_all[own]); ids = np.ascontiguousarray(ids_all[own]); n = len(xyz)
+assert n > 3 * 2048                  # several tiles: the per-tile bases matter
+exp_up = ids[(xyz[:, 1] - center_e) > y_hi - reach]; exp_down = ids[(xyz[:, 1] - center_e) < y_lo + reach]
+assert len(exp_up) > 100 and len(exp_down) > 100
+def run(capacity, have_prev, have_next, stamp):
+    g = stripe_map()
+    amb.check(L.amb_dsm_set_density_hint(g.context(), len(xyz_all) / float(rows * cols)), g.context())
+    up = np.zeros(32 * (capacity + 1), np.uint8); down = np.zeros(32 * (capacity + 1), np.uint8)
+    st = L.amb_emu_self_push(g.context(), xyz.ctypes.data, ids.ctypes.data, n, 1, center_e, 0.0, capacity, have_prev, have_next,
+                             stamp, up.ctypes.data, down.ctypes.data)
+    assert st == 0, st
+    g.sync(); g.download(("elevation",))
+    return up, down, g["elevation"][:, c0:c1].copy()
+def parse(seg, capacity):
+    hdr = seg[:8].view(np.uint64)[0]
+    count, stamp = int(hdr & 0xffffffff), int(hdr >> 32)
+    rec = seg[32:32 + 32 * min(count, capacity)].view(np.float64).reshape(-1, 4)
+    return count, stamp, rec, rec[:, 3].copy().view(np.uint64)
+cap = 20000
+up, down, elev = run(cap, 1, 1, 41)
+for seg, exp, name in ((up, exp_up, "up"), (down, exp_down, "down")):
+    count, stamp, rec, rid = parse(seg, cap)
+    assert count == len(exp) and stamp == 41, (name, count, len(exp), stamp)
+    order = np.argsort(rid)
+    assert np.array_equal(rid[order], np.sort(exp)), name
+    src = xyz[np.searchsorted(ids, rid[order])]          # ids are increasing in the own array
+    assert np.array_equal(rec[order][:, :3], src), name    # raw (unshifted) coordinates, bit for bit
+# one neighbour only: the other segment stays untouched
+up1, down1, elev1 = run(cap, 0, 1, 5)
+assert not up1.any() and parse(down1, cap)[0] == len(exp_down) and parse(down1, cap)[1] == 5
+# a segment that is too small: the true count is published (the consumer raises the overflow flag), slots stay in range
+small = 64
+up2, down2, _ = run(small, 1, 1, 9)
+c2, s2, rec2, rid2 = parse(up2, small)
+assert c2 == len(exp_up) and s2 == 9 and len(rid2) == small and np.isin(rid2, exp_up).all()
+# the push changes nothing in the binning: same elevation as the plain entry point on the same points
+g0 = stripe_map()
+amb.check(L.amb_dsm_set_density_hint(g0.context(), len(xyz_all) / float(rows * cols)), g0.context())
+amb.check(L.amb_dsm_process_device_ids(g0.context(), xyz.ctypes.data, ids.ctypes.data, n, 1, center_e, 0.0), g0.context())
+g0.sync(); g0.download(("elevation",))
+ref = g0["elevation"][:, c0:c1]
+assert np.array_equal(elev.view(np.uint32), ref.view(np.uint32)) and np.array_equal(elev1.view(np.uint32), ref.view(np.uint32))
+print(json.dumps({"n_own": int(n), "up": int(len(exp_up)), "down": int(len(exp_down))}))
+''' % (ROOT, ROOT)
+    script = tmp_path / "self_push.py"
+    script.write_text(code)
+    for sched in (None, "reverse"):
+        env = dict(os.environ, AMB_TEST_EMU="1")
+        if sched:
+            env["AMB_EMU_SCHED"] = sched
+        r = subprocess.run([sys.executable, str(script)], cwd=ROOT, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        assert info["n_own"] > 6000 and info["up"] > 100 and info["down"] > 100
