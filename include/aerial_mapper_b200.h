@@ -369,7 +369,15 @@ int amb_multi_ortho_process(amb_multi* m, const amb_camera* camera, const double
 /* ---- measurement ---- */
 int amb_get_timings(amb_ctx* ctx, amb_timings* out);
 
-/* Pinned host memory for callers that want full-rate host<->device copies inside process(). */
+/* Host memory and transfer speed.  Every host entry point (amb_dsm_process, amb_ortho_process, amb_ortho_from_pcl_process,
+ * amb_dsm_process_sharded, amb_upload_layer, amb_download_layer) accepts ordinary PAGEABLE memory — what the reference's
+ * callers own (std::vector<Eigen::Vector3d>, cv::Mat, Eigen::MatrixXf storage) — as well as page-locked memory.
+ * Pinned / registered buffers are copied directly (one asynchronous DMA at PCIe rate).  Pageable transfers of 4 MB and
+ * more are staged by the library itself: a process-wide pool of worker threads (AMB_STAGING_THREADS, default 16) moves
+ * the data through three pinned 32 MB slots per device, each slot's DMA overlapping the next slot's memcpy; the winners'
+ * frame rectangles of amb_ortho_process are packed slot-wise.  Measured 2-4x faster than the driver's own staging of
+ * pageable memory (AMB_STAGING_OFF=1 selects that, for comparison).  Host mirrors (amb_set_host_mirror) must be pinned.
+ * amb_host_alloc / amb_host_free: pinned host memory for callers that want full-rate copies inside process(). */
 int amb_host_alloc(void** ptr, size_t bytes);
 int amb_host_free(void* ptr);
 
