@@ -376,7 +376,7 @@ int amb_get_timings(amb_ctx* ctx, amb_timings* out);
  * more are staged by the library itself: a process-wide pool of worker threads (AMB_STAGING_THREADS, default 16) moves
  * the data through three pinned 32 MB slots per device, each slot's DMA overlapping the next slot's memcpy; the winners'
  * frame rectangles of amb_ortho_process are packed slot-wise.  Measured 2-4x faster than the driver's own staging of
- * pageable memory (AMB_STAGING_OFF=1 selects that, for comparison).  Host mirrors (amb_set_host_mirror) must be pinned.
+ * pageable memory (AMB_STAGING_OFF=1 selects that, for comparison).  Host mirrors (amb_set_host_mirror) should be pinned (a pageable mirror works, but its copies are the driver's and do not overlap).
  * amb_host_alloc / amb_host_free: pinned host memory for callers that want full-rate copies inside process(). */
 int amb_host_alloc(void** ptr, size_t bytes);
 int amb_host_free(void* ptr);
